@@ -1,0 +1,151 @@
+/*
+ * ivr_b200.h -- C ABI of the B200-native retrieval hot path.
+ *
+ * This is the drop-in boundary (level B2).  The reference
+ * (DMDung2k3/Intelligent-Video-Analysis-Retrieval-System) is pure Python and
+ * hands this arithmetic to third-party libraries; each entry point below names
+ * the reference call it replaces.  The Python host in
+ * intelligent-video-analysis-retrieval-system_b200/ binds these symbols with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - every function returns 0 (IVR_OK) or a negative IVR_E* code; a
+ *     thread-local message is available from ivr_last_error().
+ *   - "*_device" variants take DEVICE pointers on the handle's GPU and a
+ *     cudaStream_t (as void*; NULL = the handle's own stream) and never block
+ *     the host; the plain variants take HOST pointers, do the H2D/D2H copies
+ *     themselves and return when the outputs are written.
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     fails with IVR_ENODEVICE.
+ *   - a handle is not re-entrant (the reference serialises searches on an
+ *     RLock: core.py:873, unified_index.py:92).
+ */
+#ifndef IVR_B200_H
+#define IVR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVR_OK          0
+#define IVR_EINVAL     -1   /* bad argument (dimension mismatch, k <= 0, null pointer ...) */
+#define IVR_ENODEVICE  -2   /* no usable CUDA device / wrong architecture                 */
+#define IVR_ECUDA      -3   /* a CUDA runtime or driver call failed                        */
+#define IVR_ENOMEM     -4   /* device or pinned-host allocation failed                     */
+#define IVR_EUNSUPPORTED -5 /* argument outside the supported range (e.g. k > IVR_MAX_K)   */
+
+#define IVR_MAX_K       1024  /* reference caps SearchOptions.limit at 1000 (system.py:83-92) */
+#define IVR_MAX_WINDOW  32    /* dedup look-back window (reference default 5, config B uses 8) */
+
+/* search path selector for ivr_index_search*(): */
+#define IVR_PATH_AUTO    0
+#define IVR_PATH_STREAM  1    /* K3: SIMT streaming, <= 4 queries per pass, HBM-bound          */
+#define IVR_PATH_MMA     2    /* K1+K2: tcgen05/TMEM batched GEMM with fused top-k epilogue   */
+
+typedef struct ivr_index ivr_index;
+
+/* ---- misc -------------------------------------------------------------- */
+const char* ivr_last_error(void);
+int         ivr_version(void);
+int         ivr_device_count(int* count);
+/* name / SM count / total bytes of a device (any pointer may be NULL) */
+int         ivr_device_info(int device, char* name, size_t name_len, int* sm_count,
+                            int* cc_major, int* cc_minor, size_t* total_bytes);
+
+/* ---- flat inner-product index ------------------------------------------
+ * Replaces faiss.IndexFlatIP(dim) + .add + .ntotal + .reset
+ *   (unified_index.py:1767, 1779; core.py:1208, 827, 843, 268).
+ * Rows are stored row-major in HBM as bf16 (dim padded to a multiple of 64);
+ * ids are the insertion order 0..ntotal-1.
+ */
+int     ivr_index_create(int dim, int device, ivr_index** out);
+int     ivr_index_destroy(ivr_index* idx);
+int     ivr_index_reserve(ivr_index* idx, int64_t n_rows);           /* pre-size, avoids regrowth */
+int     ivr_index_add(ivr_index* idx, const float* x_host, int64_t n);
+int     ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* stream);
+int     ivr_index_reset(ivr_index* idx);
+int64_t ivr_index_ntotal(const ivr_index* idx);
+int     ivr_index_dim(const ivr_index* idx);
+int     ivr_index_device(const ivr_index* idx);
+
+/* Replaces D, I = index.search(x, k)  (unified_index.py:503; core.py:891; system.py:1330).
+ *   q      float32 [nq, dim] row-major
+ *   D      float32 [nq, k]   inner products, descending
+ *   I      int64   [nq, k]   row ids + id_offset; -1 (score -FLT_MAX) where k > ntotal
+ * id_offset lets a row shard report global ids (multi-GPU row sharding).
+ */
+int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k,
+                     float* D_host, int64_t* I_host, int path);
+int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
+                            float* D_dev, int64_t* I_dev, int64_t id_offset, int path,
+                            void* stream);
+
+/* Kernel timing of the LAST ivr_index_search_device call (CUDA events recorded on
+ * the launching stream, only when enabled).  ms[0] = dominant scoring+select kernel,
+ * ms[1] = top-k merge kernel(s), ms[2] = query preparation; launches[0..2] = launch
+ * counts of the same.  Blocks until those events have completed. */
+int ivr_index_set_timing(ivr_index* idx, int enable);
+int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]);
+/* which path the last search took (IVR_PATH_STREAM / IVR_PATH_MMA) */
+int ivr_index_last_path(const ivr_index* idx);
+
+/* K5: merge per-shard top-k lists after the all-gather
+ * (semantic precedent: system.py:1721-1746 concat + sort + truncate).
+ *   D_parts float32 [n_parts, nq, k], I_parts int64 [n_parts, nq, k] (device),
+ *   entries with id < 0 are padding.  Output descending, ties -> lower id. */
+int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
+                          int64_t nq, int k, float* D_out, int64_t* I_out, void* stream);
+
+/* Replaces faiss.normalize_L2(x) (unified_index.py:1776): in-place row L2
+ * normalisation, zero rows untouched. */
+int ivr_normalize_l2(int device, float* x_host, int64_t n, int d);
+int ivr_normalize_l2_device(int device, float* x_dev, int64_t n, int d, void* stream);
+
+/* ---- near-duplicate keyframe pruning ------------------------------------
+ * All cosines follow sklearn's order of operations (normalise rows, then dot)
+ * in fp32, as the reference does through sklearn.metrics.pairwise.
+ */
+
+/* Replaces filter.calculate_similarities (filter.py:142-151) and the loop in
+ * TemporalAnalyzer.detect_scene_boundaries (core.py:3612-3616):
+ *   out[i-1] = cos(e[i-1], e[i]),  i = 1..n-1.   e: float32 [n, d]. */
+int ivr_consecutive_cosine(int device, const float* e_host, int64_t n, int d, float* out_host);
+int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int d,
+                                  float* out_dev, void* stream);
+
+/* Replaces filter.filter_similar_frames_advanced applied per scene by
+ * filter.apply_similarity_filtering_to_scenes (filter.py:224-259, 261-315):
+ * within each inclusive scene [scene_start[s], scene_end[s]] keep the first
+ * frame; drop frame i iff some ALREADY KEPT j in [i-min(window,len), i) has
+ * cos(e_i, e_j) >= thr.  keep[i] = 1/0; frames outside every scene get 0.
+ * Also writes cos_prev[i] = cos(e_i, e_{i-1}) (cos_prev[0] = 1) if non-NULL. */
+int ivr_dedup_window(int device, const float* e_host, int64_t n, int d,
+                     const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
+                     int window, float thr, uint8_t* keep_host, float* cos_prev_host);
+int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, int d,
+                            const int64_t* scene_start_dev, const int64_t* scene_end_dev,
+                            int64_t n_scenes, int window, float thr,
+                            uint8_t* keep_dev, float* cos_prev_dev, uint32_t* mask_ws_dev,
+                            void* stream);
+/* Timing of the last ivr_dedup_window_device call on this thread (events on the
+ * launching stream): ms[0] = banded-cosine kernel, ms[1] = greedy resolve kernel. */
+int ivr_dedup_set_timing(int enable);
+int ivr_dedup_last_timing(float ms[2]);
+
+/* Replaces filter.filter_similar_frames_in_scene (filter.py:178-222) when
+ * force_last != 0, and the video_frame_filter.extract_unique_frames rule
+ * (video_frame_filter.py:63-70) when force_last == 0 and min_distance == 1:
+ * per scene keep frame 0; then keep i iff i - last_kept >= min_distance and
+ * cos(e_i, e_last_kept) < thr; with force_last the scene's last frame is kept. */
+int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d,
+                    const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
+                    int min_distance, float thr, int force_last, uint8_t* keep_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVR_B200_H */

@@ -1,0 +1,459 @@
+// capi.cu -- the extern "C" surface declared in include/ivr_b200.h.
+#include "index.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+namespace ivr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// other translation units
+int convert_rows(ivr_index* idx, const float* src_dev, int64_t n, int64_t dst_row, cudaStream_t st);
+int normalize_l2_device(float* x_dev, int64_t n, int d, cudaStream_t st);
+int pack_parts(const float* D, const int64_t* I, uint64_t* keys, int64_t n, cudaStream_t st);
+int dedup_set_timing(int enable);
+int dedup_last_timing(float ms[2]);
+int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, uint32_t* masks,
+                  float* cos_prev, int sm_count, cudaStream_t st);
+int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
+                        const int64_t* scene_start_dev, const int64_t* scene_end_dev,
+                        int64_t n_scenes, int window, float thr, uint8_t* keep_dev,
+                        float* cos_prev_dev, uint32_t* mask_ws_dev, cudaStream_t st);
+int dedup_chain_device(const float* e_dev, int64_t n, int d, const int64_t* scene_start_dev,
+                       const int64_t* scene_end_dev, int64_t n_scenes, int min_distance, float thr,
+                       int force_last, uint8_t* keep_dev, cudaStream_t st);
+
+static int require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return IVR_ENODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (have %d)", device, n);
+        return IVR_EINVAL;
+    }
+    int major = 0;
+    IVR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; kernels are built for sm_100a only", device, major);
+        return IVR_ENODEVICE;
+    }
+    IVR_CUDA(cudaSetDevice(device));
+    return IVR_OK;
+}
+
+// scoped device buffer for the host-pointer dedup / normalise entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        IVR_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        return IVR_OK;
+    }
+};
+
+}  // namespace ivr
+
+using namespace ivr;
+
+extern "C" {
+
+const char* ivr_last_error(void) { return g_err; }
+int ivr_version(void) { return 100; }
+
+int ivr_device_count(int* count) {
+    if (!count) { set_error("count is NULL"); return IVR_EINVAL; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return IVR_OK;
+}
+
+int ivr_device_info(int device, char* name, size_t name_len, int* sm_count, int* cc_major,
+                    int* cc_minor, size_t* total_bytes) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        set_error("device %d not available", device);
+        return IVR_ENODEVICE;
+    }
+    cudaDeviceProp p;
+    IVR_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name && name_len) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_bytes) *total_bytes = p.totalGlobalMem;
+    return IVR_OK;
+}
+
+// ---------------------------------------------------------------- index ----
+int ivr_index_create(int dim, int device, ivr_index** out) {
+    if (!out) { set_error("out is NULL"); return IVR_EINVAL; }
+    *out = nullptr;
+    if (dim <= 0 || dim > 8192) { set_error("dim %d out of range (1..8192)", dim); return IVR_EINVAL; }
+    IVR_TRY(require_device(device));
+    ivr_index* idx = new (std::nothrow) ivr_index();
+    if (!idx) { set_error("out of host memory"); return IVR_ENOMEM; }
+    idx->dim = dim;
+    idx->dpad = pad_dim(dim);
+    idx->device = device;
+    cudaError_t e = cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&idx->ev[i]);
+    if (e != cudaSuccess) {
+        set_error("index_create: %s", cudaGetErrorString(e));
+        delete idx;
+        return IVR_ECUDA;
+    }
+    *out = idx;
+    return IVR_OK;
+}
+
+int ivr_index_destroy(ivr_index* idx) {
+    if (!idx) return IVR_OK;
+    cudaSetDevice(idx->device);
+    cudaDeviceSynchronize();
+    if (idx->rows) cudaFree(idx->rows);
+    if (idx->ws) cudaFree(idx->ws);
+    if (idx->io) cudaFree(idx->io);
+    if (idx->pin) cudaFreeHost(idx->pin);
+    for (auto& ev : idx->ev) if (ev) cudaEventDestroy(ev);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+    return IVR_OK;
+}
+
+int ivr_index_reserve(ivr_index* idx, int64_t n_rows) {
+    if (!idx || n_rows < 0) { set_error("reserve: bad argument"); return IVR_EINVAL; }
+    if (n_rows > 0x7fffffff) { set_error("a shard holds at most 2^31-1 rows"); return IVR_EUNSUPPORTED; }
+    IVR_CUDA(cudaSetDevice(idx->device));
+    return ensure_capacity(idx, n_rows, idx->stream, /*exact=*/true);
+}
+
+int ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* stream) {
+    if (!idx || n < 0 || (n > 0 && !x_dev)) { set_error("add_device: bad argument"); return IVR_EINVAL; }
+    if (n == 0) return IVR_OK;
+    IVR_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : idx->stream;
+    if (idx->ntotal + n > 0x7fffffff) { set_error("a shard holds at most 2^31-1 rows"); return IVR_EUNSUPPORTED; }
+    IVR_TRY(ensure_capacity(idx, idx->ntotal + n, st));
+    IVR_TRY(convert_rows(idx, x_dev, n, idx->ntotal, st));
+    idx->ntotal += n;
+    return IVR_OK;
+}
+
+int ivr_index_add(ivr_index* idx, const float* x_host, int64_t n) {
+    if (!idx || n < 0 || (n > 0 && !x_host)) { set_error("add: bad argument"); return IVR_EINVAL; }
+    if (n == 0) return IVR_OK;
+    IVR_CUDA(cudaSetDevice(idx->device));
+    if (idx->ntotal + n > 0x7fffffff) { set_error("a shard holds at most 2^31-1 rows"); return IVR_EUNSUPPORTED; }
+    cudaStream_t st = idx->stream;
+    IVR_TRY(ensure_capacity(idx, idx->ntotal + n, st));
+    // stage through two pinned half-buffers + a device fp32 staging area in the workspace
+    const size_t row_bytes = static_cast<size_t>(idx->dim) * sizeof(float);
+    int64_t chunk = std::max<int64_t>(1, (static_cast<int64_t>(32) << 20) / static_cast<int64_t>(row_bytes));
+    chunk = std::min(chunk, n);
+    IVR_TRY(ensure_pin(idx, 2 * chunk * row_bytes));
+    IVR_TRY(ensure_ws(idx, 2 * chunk * row_bytes));
+    cudaEvent_t done[2];
+    for (auto& e : done) IVR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = IVR_OK;
+    int64_t off = 0;
+    for (int it = 0; off < n; ++it) {
+        const int64_t m = std::min(chunk, n - off);
+        const int b = it & 1;
+        char* pin = static_cast<char*>(idx->pin) + b * chunk * row_bytes;
+        float* dev = reinterpret_cast<float*>(static_cast<char*>(idx->ws) + b * chunk * row_bytes);
+        if (it >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = IVR_ECUDA; break; }
+        memcpy(pin, x_host + off * idx->dim, m * row_bytes);
+        if (cudaMemcpyAsync(dev, pin, m * row_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = IVR_ECUDA; break; }
+        rc = convert_rows(idx, dev, m, idx->ntotal + off, st);
+        if (rc != IVR_OK) break;
+        cudaEventRecord(done[b], st);
+        off += m;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (auto& ev : done) cudaEventDestroy(ev);
+    if (rc == IVR_OK && e != cudaSuccess) { set_error("add: %s", cudaGetErrorString(e)); rc = IVR_ECUDA; }
+    if (rc == IVR_ECUDA && g_err[0] == 0) set_error("add: CUDA failure");
+    if (rc == IVR_OK) idx->ntotal += n;
+    return rc;
+}
+
+int ivr_index_reset(ivr_index* idx) {
+    if (!idx) { set_error("reset: NULL index"); return IVR_EINVAL; }
+    idx->ntotal = 0;
+    return IVR_OK;
+}
+
+int64_t ivr_index_ntotal(const ivr_index* idx) { return idx ? idx->ntotal : -1; }
+int ivr_index_dim(const ivr_index* idx) { return idx ? idx->dim : -1; }
+int ivr_index_device(const ivr_index* idx) { return idx ? idx->device : -1; }
+
+// --------------------------------------------------------------- search ----
+__global__ void fill_empty_kernel(float* D, int64_t* I, int64_t n) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) { D[i] = -3.402823466e+38f; I[i] = -1; }
+}
+
+int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                            int64_t* I_dev, int64_t id_offset, int path, void* stream) {
+    if (!idx || nq < 0 || (nq > 0 && (!q_dev || !D_dev || !I_dev))) {
+        set_error("search: bad argument");
+        return IVR_EINVAL;
+    }
+    if (k <= 0) { set_error("search: k must be positive (got %d)", k); return IVR_EINVAL; }
+    if (k > IVR_MAX_K) { set_error("search: k=%d exceeds IVR_MAX_K=%d", k, IVR_MAX_K); return IVR_EUNSUPPORTED; }
+    if (nq == 0) return IVR_OK;
+    IVR_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : idx->stream;
+    idx->launches[0] = idx->launches[1] = idx->launches[2] = 0;
+    idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = false;
+    if (idx->ntotal == 0) {
+        const int64_t n = nq * k;
+        fill_empty_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(D_dev, I_dev, n);
+        IVR_CUDA(cudaGetLastError());
+        idx->last_path = 0;
+        return IVR_OK;
+    }
+    int use = path;
+    if (use == IVR_PATH_AUTO) use = (nq > 4 && mma_supported(idx, nq, k)) ? IVR_PATH_MMA : IVR_PATH_STREAM;
+    if (use == IVR_PATH_MMA) {
+        if (!mma_supported(idx, nq, k)) {
+            set_error("search: the tcgen05 path does not support dim=%d k=%d", idx->dim, k);
+            return IVR_EUNSUPPORTED;
+        }
+        idx->last_path = IVR_PATH_MMA;
+        return search_mma(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
+    }
+    if (use != IVR_PATH_STREAM) { set_error("search: unknown path %d", path); return IVR_EINVAL; }
+    idx->last_path = IVR_PATH_STREAM;
+    return search_stream(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
+}
+
+int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k, float* D_host,
+                     int64_t* I_host, int path) {
+    if (!idx || nq < 0 || (nq > 0 && (!q_host || !D_host || !I_host))) {
+        set_error("search: bad argument");
+        return IVR_EINVAL;
+    }
+    if (k <= 0) { set_error("search: k must be positive (got %d)", k); return IVR_EINVAL; }
+    if (k > IVR_MAX_K) { set_error("search: k=%d exceeds IVR_MAX_K=%d", k, IVR_MAX_K); return IVR_EUNSUPPORTED; }
+    if (nq == 0) return IVR_OK;
+    IVR_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    const size_t qb = static_cast<size_t>(nq) * idx->dim * sizeof(float);
+    const size_t db = static_cast<size_t>(nq) * k * sizeof(float);
+    const size_t ib = static_cast<size_t>(nq) * k * sizeof(int64_t);
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    IVR_TRY(ensure_pin(idx, up(qb) + up(db) + up(ib)));
+    char* pin = static_cast<char*>(idx->pin);
+    IVR_TRY(ensure_io(idx, up(qb) + up(db) + up(ib)));
+    char* io = static_cast<char*>(idx->io);
+    float* dq = reinterpret_cast<float*>(io);
+    float* dd = reinterpret_cast<float*>(io + up(qb));
+    int64_t* di = reinterpret_cast<int64_t*>(io + up(qb) + up(db));
+    memcpy(pin, q_host, qb);
+    IVR_CUDA(cudaMemcpyAsync(dq, pin, qb, cudaMemcpyHostToDevice, st));
+    IVR_TRY(ivr_index_search_device(idx, dq, nq, k, dd, di, 0, path, st));
+    IVR_CUDA(cudaMemcpyAsync(pin + up(qb), dd, db, cudaMemcpyDeviceToHost, st));
+    IVR_CUDA(cudaMemcpyAsync(pin + up(qb) + up(db), di, ib, cudaMemcpyDeviceToHost, st));
+    IVR_CUDA(cudaStreamSynchronize(st));
+    memcpy(D_host, pin + up(qb), db);
+    memcpy(I_host, pin + up(qb) + up(db), ib);
+    return IVR_OK;
+}
+
+int ivr_index_set_timing(ivr_index* idx, int enable) {
+    if (!idx) { set_error("NULL index"); return IVR_EINVAL; }
+    idx->timing = enable != 0;
+    return IVR_OK;
+}
+
+int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]) {
+    if (!idx || !ms) { set_error("last_timing: bad argument"); return IVR_EINVAL; }
+    IVR_CUDA(cudaSetDevice(idx->device));
+    for (int i = 0; i < 3; ++i) {
+        ms[i] = 0.f;
+        if (idx->ev_valid[i]) {
+            IVR_CUDA(cudaEventSynchronize(idx->ev[2 * i + 1]));
+            IVR_CUDA(cudaEventElapsedTime(&ms[i], idx->ev[2 * i], idx->ev[2 * i + 1]));
+        }
+        if (launches) launches[i] = idx->launches[i];
+    }
+    return IVR_OK;
+}
+
+int ivr_index_last_path(const ivr_index* idx) { return idx ? idx->last_path : -1; }
+
+int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
+                          int64_t nq, int k, float* D_out, int64_t* I_out, void* stream) {
+    if (n_parts <= 0 || nq < 0 || k <= 0 || !D_parts || !I_parts || !D_out || !I_out) {
+        set_error("topk_merge: bad argument");
+        return IVR_EINVAL;
+    }
+    if (k > IVR_MAX_K) { set_error("topk_merge: k=%d exceeds IVR_MAX_K", k); return IVR_EUNSUPPORTED; }
+    if (nq == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = static_cast<int64_t>(n_parts) * nq * k;
+    const size_t tmp_keys = merge_tmp_entries(n_parts, nq, k);
+    uint64_t* keys = nullptr;
+    IVR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&keys), (n + tmp_keys) * sizeof(uint64_t) +
+                             (static_cast<size_t>(n_parts) * nq + 64) * sizeof(int), st));
+    int rc = pack_parts(D_parts, I_parts, keys, n, st);
+    if (rc == IVR_OK) {
+        MergeIn in{};
+        in.entries = keys; in.counts = nullptr;
+        in.list_stride = nq * k; in.q_stride = k;
+        in.n_lists = n_parts; in.fixed_count = k;
+        rc = merge_lists_final(in, nq, k, D_out, I_out, 0, keys + n,
+                               reinterpret_cast<int*>(keys + n + tmp_keys), st, nullptr);
+    }
+    cudaFreeAsync(keys, st);
+    return rc;
+}
+
+// ------------------------------------------------------------ normalise ----
+int ivr_normalize_l2_device(int device, float* x_dev, int64_t n, int d, void* stream) {
+    if (n < 0 || d <= 0 || (n > 0 && !x_dev)) { set_error("normalize_l2: bad argument"); return IVR_EINVAL; }
+    IVR_TRY(require_device(device));
+    return normalize_l2_device(x_dev, n, d, static_cast<cudaStream_t>(stream));
+}
+
+int ivr_normalize_l2(int device, float* x_host, int64_t n, int d) {
+    if (n < 0 || d <= 0 || (n > 0 && !x_host)) { set_error("normalize_l2: bad argument"); return IVR_EINVAL; }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
+    DevBuf b;
+    IVR_TRY(b.alloc(bytes));
+    IVR_CUDA(cudaMemcpy(b.p, x_host, bytes, cudaMemcpyHostToDevice));
+    IVR_TRY(normalize_l2_device(static_cast<float*>(b.p), n, d, nullptr));
+    IVR_CUDA(cudaMemcpy(x_host, b.p, bytes, cudaMemcpyDeviceToHost));
+    return IVR_OK;
+}
+
+// ---------------------------------------------------------------- dedup ----
+int ivr_dedup_set_timing(int enable) { return dedup_set_timing(enable); }
+int ivr_dedup_last_timing(float ms[2]) { return ms ? dedup_last_timing(ms) : IVR_EINVAL; }
+
+int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int d, float* out_dev,
+                                  void* stream) {
+    // out_dev: n floats, out[i] = cos(e_i, e_{i-1}), out[0] = 1  (device variant keeps the
+    // frame-aligned layout; the host variant below drops element 0 like the reference list)
+    if (n < 0 || d <= 0 || (n > 0 && (!e_dev || !out_dev))) { set_error("consecutive_cosine: bad argument"); return IVR_EINVAL; }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    int sm = 0;
+    IVR_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    return launch_banded(e_dev, n, d, 1, 2.0f, nullptr, out_dev, sm, static_cast<cudaStream_t>(stream));
+}
+
+int ivr_consecutive_cosine(int device, const float* e_host, int64_t n, int d, float* out_host) {
+    if (n < 0 || d <= 0 || (n > 0 && !e_host) || (n > 1 && !out_host)) { set_error("consecutive_cosine: bad argument"); return IVR_EINVAL; }
+    if (n <= 1) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
+    DevBuf e, o;
+    IVR_TRY(e.alloc(bytes)); IVR_TRY(o.alloc(n * sizeof(float)));
+    IVR_CUDA(cudaMemcpy(e.p, e_host, bytes, cudaMemcpyHostToDevice));
+    IVR_TRY(ivr_consecutive_cosine_device(device, static_cast<float*>(e.p), n, d, static_cast<float*>(o.p), nullptr));
+    IVR_CUDA(cudaMemcpy(out_host, static_cast<float*>(o.p) + 1, (n - 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    return IVR_OK;
+}
+
+int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, int d,
+                            const int64_t* scene_start_dev, const int64_t* scene_end_dev,
+                            int64_t n_scenes, int window, float thr, uint8_t* keep_dev,
+                            float* cos_prev_dev, uint32_t* mask_ws_dev, void* stream) {
+    if (n < 0 || d <= 0 || n_scenes < 0 || (n > 0 && (!e_dev || !keep_dev || !mask_ws_dev)) ||
+        (n_scenes > 0 && (!scene_start_dev || !scene_end_dev))) {
+        set_error("dedup_window: bad argument");
+        return IVR_EINVAL;
+    }
+    if (window < 1 || window > IVR_MAX_WINDOW) {
+        set_error("dedup_window: window %d outside 1..%d", window, IVR_MAX_WINDOW);
+        return IVR_EUNSUPPORTED;
+    }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    return dedup_window_device(device, e_dev, n, d, scene_start_dev, scene_end_dev, n_scenes, window,
+                               thr, keep_dev, cos_prev_dev, mask_ws_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ivr_dedup_window(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
+                     const int64_t* scene_end, int64_t n_scenes, int window, float thr,
+                     uint8_t* keep_host, float* cos_prev_host) {
+    if (n < 0 || d <= 0 || n_scenes < 0 || (n > 0 && (!e_host || !keep_host)) ||
+        (n_scenes > 0 && (!scene_start || !scene_end))) {
+        set_error("dedup_window: bad argument");
+        return IVR_EINVAL;
+    }
+    if (window < 1 || window > IVR_MAX_WINDOW) {
+        set_error("dedup_window: window %d outside 1..%d", window, IVR_MAX_WINDOW);
+        return IVR_EUNSUPPORTED;
+    }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
+    DevBuf e, m, c, k, ss, se;
+    IVR_TRY(e.alloc(bytes)); IVR_TRY(m.alloc(n * sizeof(uint32_t))); IVR_TRY(c.alloc(n * sizeof(float)));
+    IVR_TRY(k.alloc(n)); IVR_TRY(ss.alloc(n_scenes * sizeof(int64_t))); IVR_TRY(se.alloc(n_scenes * sizeof(int64_t)));
+    IVR_CUDA(cudaMemcpy(e.p, e_host, bytes, cudaMemcpyHostToDevice));
+    if (n_scenes > 0) {
+        IVR_CUDA(cudaMemcpy(ss.p, scene_start, n_scenes * sizeof(int64_t), cudaMemcpyHostToDevice));
+        IVR_CUDA(cudaMemcpy(se.p, scene_end, n_scenes * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    IVR_TRY(dedup_window_device(device, static_cast<float*>(e.p), n, d, static_cast<int64_t*>(ss.p),
+                                static_cast<int64_t*>(se.p), n_scenes, window, thr,
+                                static_cast<uint8_t*>(k.p), static_cast<float*>(c.p),
+                                static_cast<uint32_t*>(m.p), nullptr));
+    IVR_CUDA(cudaMemcpy(keep_host, k.p, n, cudaMemcpyDeviceToHost));
+    if (cos_prev_host) IVR_CUDA(cudaMemcpy(cos_prev_host, c.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return IVR_OK;
+}
+
+int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
+                    const int64_t* scene_end, int64_t n_scenes, int min_distance, float thr,
+                    int force_last, uint8_t* keep_host) {
+    if (n < 0 || d <= 0 || n_scenes < 0 || (n > 0 && (!e_host || !keep_host)) ||
+        (n_scenes > 0 && (!scene_start || !scene_end))) {
+        set_error("dedup_chain: bad argument");
+        return IVR_EINVAL;
+    }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
+    DevBuf e, k, ss, se;
+    IVR_TRY(e.alloc(bytes)); IVR_TRY(k.alloc(n));
+    IVR_TRY(ss.alloc(n_scenes * sizeof(int64_t))); IVR_TRY(se.alloc(n_scenes * sizeof(int64_t)));
+    IVR_CUDA(cudaMemcpy(e.p, e_host, bytes, cudaMemcpyHostToDevice));
+    if (n_scenes > 0) {
+        IVR_CUDA(cudaMemcpy(ss.p, scene_start, n_scenes * sizeof(int64_t), cudaMemcpyHostToDevice));
+        IVR_CUDA(cudaMemcpy(se.p, scene_end, n_scenes * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    IVR_TRY(dedup_chain_device(static_cast<float*>(e.p), n, d, static_cast<int64_t*>(ss.p),
+                               static_cast<int64_t*>(se.p), n_scenes, min_distance, thr, force_last,
+                               static_cast<uint8_t*>(k.p), nullptr));
+    IVR_CUDA(cudaMemcpy(keep_host, k.p, n, cudaMemcpyDeviceToHost));
+    return IVR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// dedup.cu -- K4: fused normalise-and-compare kernels for near-duplicate pruning.
+//
+// Reference rules replaced (all cosines are sklearn.metrics.pairwise.cosine_similarity
+// on two 1xD float32 rows: normalise each row, then dot):
+//   filter.calculate_similarities            filter.py:142-151   (consecutive cosine)
+//   filter.filter_similar_frames_advanced    filter.py:224-259   (window rule)
+//   filter.filter_similar_frames_in_scene    filter.py:178-222   (last-kept chain)
+//   video_frame_filter rule                  video_frame_filter.py:63-70
+//
+// banded_cosine_kernel: ONE pass over the fp32 frame matrix (HBM-bound, D*4 bytes
+// per frame).  Each warp owns one frame per batch: it loads the row with 128-bit
+// coalesced loads, normalises it in registers, parks the normalised row in a
+// shared-memory ring, and dots it against the previous W parked rows.  Output per
+// frame: a W-bit mask (bit d-1 <=> cos(e_i, e_{i-d}) >= thr) and cos(e_i, e_{i-1}).
+// window_resolve_kernel then runs the reference's sequential greedy rule per scene
+// on the bit masks alone (O(1) per frame with a W-bit keep history).
+#include "common.cuh"
+
+namespace ivr {
+
+constexpr int kDedupWarps = 8;                 // frames per batch and per CTA
+constexpr int kDedupThreads = kDedupWarps * 32;
+
+// DV > 0: d == DV*128, each lane holds DV float4 of its row.  DV == 0: generic d.
+template <int DV>
+__global__ void __launch_bounds__(kDedupThreads)
+banded_cosine_kernel(const float* __restrict__ e, int64_t n, int d, int window, float thr,
+                     uint32_t* __restrict__ masks, float* __restrict__ cos_prev, int ring) {
+    extern __shared__ float s_ring[];          // ring * dstride floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dstride = (DV > 0) ? DV * 128 : ((d + 3) / 4 * 4);
+
+    // contiguous chunk of frames per CTA (+ a halo of `window` frames re-normalised locally)
+    const int64_t f0 = n * blockIdx.x / gridDim.x, f1 = n * (blockIdx.x + 1) / gridDim.x;
+    if (f0 >= f1) return;
+    const int64_t fs = (f0 - window > 0) ? f0 - window : 0;
+
+    constexpr int NV = (DV > 0) ? DV : 1;
+    float4 cur[NV], nxt[NV];
+
+    auto load_row = [&](int64_t i, float4 (&r)[NV]) {
+        if (DV > 0) {
+            const float4* p = reinterpret_cast<const float4*>(e + i * d);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) r[j] = ldg_nc_f4(p + lane + 32 * j);
+        }
+    };
+
+    int64_t base = fs;
+    if (DV > 0 && base + warp < f1) load_row(base + warp, nxt);
+
+    for (; base < f1; base += kDedupWarps) {
+        const int64_t i = base + warp;
+        const bool live = i < f1;
+        float* slot = s_ring + static_cast<size_t>((i % ring)) * dstride;
+        if (live) {
+            if (DV > 0) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) cur[j] = nxt[j];
+                if (i + kDedupWarps < f1) load_row(i + kDedupWarps, nxt);   // prefetch next batch
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    ss = fmaf(cur[j].x, cur[j].x, ss); ss = fmaf(cur[j].y, cur[j].y, ss);
+                    ss = fmaf(cur[j].z, cur[j].z, ss); ss = fmaf(cur[j].w, cur[j].w, ss);
+                }
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                float nrm = sqrtf(ss);
+                if (nrm == 0.f) nrm = 1.f;                                   // sklearn: 0 -> 1
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    cur[j].x /= nrm; cur[j].y /= nrm; cur[j].z /= nrm; cur[j].w /= nrm;
+                    reinterpret_cast<float4*>(slot)[lane + 32 * j] = cur[j];
+                }
+            } else {
+                const float* p = e + i * d;
+                float ss = 0.f;
+                for (int c = lane; c < d; c += 32) { const float v = p[c]; ss = fmaf(v, v, ss); }
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                float nrm = sqrtf(ss);
+                if (nrm == 0.f) nrm = 1.f;
+                for (int c = lane; c < d; c += 32) slot[c] = p[c] / nrm;
+            }
+        }
+        __syncthreads();
+        if (live && i >= f0) {
+            uint32_t m = 0;
+            float c1 = 1.0f;
+            for (int dd = 1; dd <= window; ++dd) {
+                const int64_t j = i - dd;
+                if (j < 0) break;
+                const float* other = s_ring + static_cast<size_t>((j % ring)) * dstride;
+                float acc = 0.f;
+                if (DV > 0) {
+#pragma unroll
+                    for (int jj = 0; jj < NV; ++jj) {
+                        const float4 o = reinterpret_cast<const float4*>(other)[lane + 32 * jj];
+                        acc = fmaf(cur[jj].x, o.x, acc); acc = fmaf(cur[jj].y, o.y, acc);
+                        acc = fmaf(cur[jj].z, o.z, acc); acc = fmaf(cur[jj].w, o.w, acc);
+                    }
+                } else {
+                    for (int c = lane; c < d; c += 32) acc = fmaf(slot[c], other[c], acc);
+                }
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (acc >= thr) m |= 1u << (dd - 1);
+                if (dd == 1) c1 = acc;
+            }
+            if (lane == 0) {
+                if (masks) masks[i] = m;
+                if (cos_prev) cos_prev[i] = c1;
+            }
+        }
+        // ring holds window + 2 batches: the next batch's writes cannot touch rows this
+        // batch still reads, so one barrier per batch is enough.
+    }
+}
+
+// One thread per scene: the reference's greedy rule on the bit masks.
+//   keep_i = !exists d in [1, min(window, i - scene_start)] : keep_{i-d} && bit_{d-1}(mask_i)
+__global__ void window_resolve_kernel(const uint32_t* __restrict__ masks,
+                                      const int64_t* __restrict__ scene_start,
+                                      const int64_t* __restrict__ scene_end, int64_t n_scenes,
+                                      int64_t n, int window, uint8_t* __restrict__ keep) {
+    const int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (s >= n_scenes) return;
+    int64_t a = scene_start[s], b = scene_end[s];
+    if (a < 0) a = 0;
+    if (b >= n) b = n - 1;
+    const uint32_t wmask = (window >= 32) ? 0xffffffffu : ((1u << window) - 1u);
+    uint32_t hist = 0;                          // bit d-1 = keep flag of frame i-d (this scene only)
+    for (int64_t i = a; i <= b; ++i) {
+        const uint32_t k = ((masks[i] & hist & wmask) == 0u) ? 1u : 0u;
+        keep[i] = static_cast<uint8_t>(k);
+        hist = (hist << 1) | k;                 // frames before the scene start are never set
+    }
+}
+
+// One warp per scene: last-kept chain (filter.py:178-222 / video_frame_filter.py:63-70).
+__global__ void chain_resolve_kernel(const float* __restrict__ e, int d,
+                                     const int64_t* __restrict__ scene_start,
+                                     const int64_t* __restrict__ scene_end, int64_t n_scenes,
+                                     int64_t n, int min_distance, float thr, int force_last,
+                                     uint8_t* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (s >= n_scenes) return;
+    int64_t a = scene_start[s], b = scene_end[s];
+    if (a < 0) a = 0;
+    if (b >= n) b = n - 1;
+    if (a > b) return;
+    auto norm_of = [&](int64_t i) {
+        const float* p = e + i * d;
+        float ss = 0.f;
+        for (int c = lane; c < d; c += 32) { const float v = p[c]; ss = fmaf(v, v, ss); }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        float nrm = sqrtf(ss);
+        return nrm == 0.f ? 1.f : nrm;
+    };
+    int64_t last = a;
+    float nlast = norm_of(a);
+    if (lane == 0) keep[a] = 1;
+    for (int64_t i = a + 1; i <= b; ++i) {
+        if (i - last < min_distance) { if (lane == 0) keep[i] = 0; continue; }
+        const float ni = norm_of(i);
+        const float* p = e + i * d;
+        const float* q = e + last * d;
+        float acc = 0.f;
+        for (int c = lane; c < d; c += 32) acc = fmaf(p[c] / ni, q[c] / nlast, acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const bool k = acc < thr;
+        if (lane == 0) keep[i] = k ? 1 : 0;
+        if (k) { last = i; nlast = ni; }
+    }
+    if (force_last && last != b && lane == 0) keep[b] = 1;
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+static thread_local bool        g_dedup_timing = false;
+static thread_local cudaEvent_t g_dedup_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local bool        g_dedup_ev_valid = false;
+
+int dedup_set_timing(int enable) { g_dedup_timing = enable != 0; return IVR_OK; }
+
+int dedup_last_timing(float ms[2]) {
+    if (!g_dedup_ev_valid) { set_error("no timed dedup call on this thread"); return IVR_EINVAL; }
+    IVR_CUDA(cudaEventSynchronize(g_dedup_ev[3]));
+    IVR_CUDA(cudaEventElapsedTime(&ms[0], g_dedup_ev[0], g_dedup_ev[1]));
+    IVR_CUDA(cudaEventElapsedTime(&ms[1], g_dedup_ev[2], g_dedup_ev[3]));
+    return IVR_OK;
+}
+
+int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, uint32_t* masks,
+                  float* cos_prev, int sm_count, cudaStream_t st) {
+    if (n <= 0) return IVR_OK;
+    const int ring = window + 2 * kDedupWarps;
+    int dv = 0;
+    if (d % 128 == 0 && (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0) dv = d / 128;
+    const int dstride = dv ? d : (d + 3) / 4 * 4;
+    const size_t smem = static_cast<size_t>(ring) * dstride * sizeof(float);
+    if (smem > 227 * 1024) {
+        set_error("dedup: window %d x dim %d needs %zu B of shared memory (> 227 KB)", window, d, smem);
+        return IVR_EUNSUPPORTED;
+    }
+    // enough CTAs to fill the machine twice over, but chunks of at least 64 frames so the
+    // re-normalised halo stays a small fraction of the work
+    int64_t grid = static_cast<int64_t>(sm_count) * 4;
+    const int64_t max_grid = (n + 63) / 64;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+#define IVR_LAUNCH_BANDED(DV)                                                                      \
+    do {                                                                                           \
+        auto kern = banded_cosine_kernel<DV>;                                                      \
+        if (smem > 48 * 1024)                                                                      \
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                          static_cast<int>(smem)));                                \
+        kern<<<static_cast<unsigned>(grid), kDedupThreads, smem, st>>>(e_dev, n, d, window, thr,   \
+                                                                       masks, cos_prev, ring);     \
+    } while (0)
+    switch (dv) {
+        case 3: IVR_LAUNCH_BANDED(3); break;     // 384
+        case 4: IVR_LAUNCH_BANDED(4); break;     // 512
+        case 6: IVR_LAUNCH_BANDED(6); break;     // 768
+        case 8: IVR_LAUNCH_BANDED(8); break;     // 1024
+        default: IVR_LAUNCH_BANDED(0); break;
+    }
+#undef IVR_LAUNCH_BANDED
+    IVR_CUDA(cudaGetLastError());
+    return IVR_OK;
+}
+
+int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
+                        const int64_t* scene_start_dev, const int64_t* scene_end_dev,
+                        int64_t n_scenes, int window, float thr, uint8_t* keep_dev,
+                        float* cos_prev_dev, uint32_t* mask_ws_dev, cudaStream_t st) {
+    if (n <= 0) return IVR_OK;
+    int sm_count = 0;
+    IVR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (g_dedup_timing && !g_dedup_ev[0])
+        for (auto& ev : g_dedup_ev) IVR_CUDA(cudaEventCreate(&ev));
+    if (g_dedup_timing) cudaEventRecord(g_dedup_ev[0], st);
+    IVR_TRY(launch_banded(e_dev, n, d, window, thr, mask_ws_dev, cos_prev_dev, sm_count, st));
+    if (g_dedup_timing) { cudaEventRecord(g_dedup_ev[1], st); cudaEventRecord(g_dedup_ev[2], st); }
+    IVR_CUDA(cudaMemsetAsync(keep_dev, 0, static_cast<size_t>(n), st));
+    if (n_scenes > 0) {
+        const int threads = 128;
+        window_resolve_kernel<<<static_cast<unsigned>((n_scenes + threads - 1) / threads), threads, 0, st>>>(
+            mask_ws_dev, scene_start_dev, scene_end_dev, n_scenes, n, window, keep_dev);
+        IVR_CUDA(cudaGetLastError());
+    }
+    if (g_dedup_timing) { cudaEventRecord(g_dedup_ev[3], st); g_dedup_ev_valid = true; }
+    return IVR_OK;
+}
+
+int dedup_chain_device(const float* e_dev, int64_t n, int d, const int64_t* scene_start_dev,
+                       const int64_t* scene_end_dev, int64_t n_scenes, int min_distance, float thr,
+                       int force_last, uint8_t* keep_dev, cudaStream_t st) {
+    if (n <= 0) return IVR_OK;
+    IVR_CUDA(cudaMemsetAsync(keep_dev, 0, static_cast<size_t>(n), st));
+    if (n_scenes <= 0) return IVR_OK;
+    const int threads = 128;
+    const int64_t blocks = (n_scenes * 32 + threads - 1) / threads;
+    chain_resolve_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+        e_dev, d, scene_start_dev, scene_end_dev, n_scenes, n, min_distance, thr, force_last, keep_dev);
+    IVR_CUDA(cudaGetLastError());
+    return IVR_OK;
+}
+
+}  // namespace ivr

@@ -1,0 +1,71 @@
+// index.cuh -- the flat inner-product index handle (device-resident bf16 rows).
+#pragma once
+
+#include "common.cuh"
+
+struct ivr_index {
+    int      dim      = 0;        // logical dimension (as given by the caller)
+    int      dpad     = 0;        // storage dimension: dim padded to a multiple of 64
+    int      device   = 0;
+    int      sm_count = 0;
+    int64_t  ntotal   = 0;
+    int64_t  capacity = 0;        // rows allocated
+    __nv_bfloat16* rows = nullptr;   // [capacity, dpad] row-major, HBM
+
+    cudaStream_t stream = nullptr;   // handle-owned stream for the host-pointer entry points
+
+    // scratch, grown on demand (device)
+    void*   ws      = nullptr;
+    size_t  ws_bytes = 0;
+    // device staging for the host-pointer search entry point (queries in, D/I out)
+    void*   io       = nullptr;
+    size_t  io_bytes = 0;
+    // pinned host staging
+    void*   pin      = nullptr;
+    size_t  pin_bytes = 0;
+
+    // TMA descriptor cache for the MMA path (opaque 128-byte CUtensorMap blobs)
+    alignas(64) unsigned char tmap_rows[128];
+    const void* tmap_rows_base = nullptr;
+    int64_t     tmap_rows_n    = -1;
+
+    // timing of the last device search
+    bool        timing = false;
+    cudaEvent_t ev[6]  = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool        ev_valid[3] = {false, false, false};
+    int         launches[3] = {0, 0, 0};
+    int         last_path = 0;
+};
+
+namespace ivr {
+
+int  ensure_ws(ivr_index* idx, size_t bytes);
+int  ensure_pin(ivr_index* idx, size_t bytes);
+int  ensure_io(ivr_index* idx, size_t bytes);
+int  ensure_capacity(ivr_index* idx, int64_t rows, cudaStream_t st, bool exact = false);
+
+// search back-ends (search_stream.cu / search_mma.cu / topk_merge.cu)
+int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                  int64_t* I_dev, int64_t id_offset, cudaStream_t st);
+int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+               int64_t* I_dev, int64_t id_offset, cudaStream_t st);
+bool mma_supported(const ivr_index* idx, int64_t nq, int k);
+
+// Generic list merge.  For query q, list l lives at entries + l*list_stride + q*q_stride
+// (64-bit keys) and holds counts[l*cnt_list_stride + q*cnt_q_stride] entries (or
+// `fixed_count` entries when counts == nullptr).
+struct MergeIn {
+    const uint64_t* entries;
+    const int*      counts;
+    int64_t list_stride, q_stride;
+    int64_t cnt_list_stride, cnt_q_stride;
+    int     n_lists;
+    int     fixed_count;
+};
+// final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset
+int merge_lists_final(const MergeIn& in, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                      int64_t id_offset, uint64_t* tmp_entries, int* tmp_counts,
+                      cudaStream_t st, int* n_launches);
+size_t merge_tmp_entries(int n_lists, int64_t nq, int k);   // #keys of scratch the merge may need
+
+}  // namespace ivr

@@ -1,0 +1,105 @@
+"""Import shims that run the REFERENCE'S OWN files in the authoring container.
+
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (and optional
+local cross-checks) to produce golden vectors from the unmodified reference at
+/root/reference.  Nothing here is read at run time on the GPU box, where
+/root/reference does not exist; no reference source is copied into the repo.
+
+What is shimmed and why:
+  * ``transformers``  -- filter.py:46-48 calls ``from_pretrained`` at import
+                         (network); a stub class is injected instead.
+  * ``faiss``         -- unified_index.py:31 / core.py:32 import it
+                         unconditionally; not installed.  A caller-supplied
+                         faiss-shaped module (the oracle's, or the product's
+                         ``faiss_compat``) is injected.
+  * ``h5py``, ``lz4``, ``lz4.frame`` -- unified_index.py:29-30; empty stubs
+                         (only the .rvdb I/O uses them, which is out of scope).
+  * CWD               -- ``utils.Config()`` creates exports/ index/ logs/
+                         metadata/ relative to the CWD (utils.py:267-268), so the
+                         import happens inside a temp dir.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import os
+import sys
+import tempfile
+import types
+
+REFERENCE_DIR = os.environ.get("IVR_REFERENCE_DIR", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "filter.py"))
+
+
+def _stub_transformers():
+    tr = types.ModuleType("transformers")
+
+    class _Stub:
+        @classmethod
+        def from_pretrained(cls, *a, **k):
+            return cls()
+
+        def to(self, *a, **k):
+            return self
+
+        def eval(self):
+            return self
+
+    for name in ("AutoImageProcessor", "AutoModel", "CLIPModel", "CLIPProcessor",
+                 "CLIPTokenizer", "AutoTokenizer", "AutoProcessor"):
+        setattr(tr, name, _Stub)
+    return tr
+
+
+def oracle_faiss_module():
+    """A ``faiss``-shaped module backed by oracle.flat_ip (for pinning the wrappers)."""
+    from . import flat_ip
+    m = types.ModuleType("faiss")
+    m.IndexFlatIP = flat_ip.IndexFlatIP
+    m.Index = flat_ip.IndexFlatIP
+    m.normalize_L2 = flat_ip.normalize_L2
+    return m
+
+
+@contextlib.contextmanager
+def reference_modules(faiss_module=None, names=("filter",)):
+    """Yield a dict {name: module} of reference modules imported under shims.
+
+    Modules are removed from ``sys.modules`` again on exit so the product's own
+    same-named modules are never shadowed.
+    """
+    if not reference_available():
+        raise RuntimeError(f"reference not present at {REFERENCE_DIR}")
+    saved = {k: sys.modules.get(k) for k in
+             ("transformers", "faiss", "h5py", "lz4", "lz4.frame",
+              "filter", "core", "utils", "unified_index", "unified_builder")}
+    old_path = list(sys.path)
+    old_cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="ivr_ref_")
+    try:
+        if "filter" in names:
+            sys.modules["transformers"] = _stub_transformers()
+        sys.modules["faiss"] = faiss_module or oracle_faiss_module()
+        for stub in ("h5py", "lz4", "lz4.frame"):
+            mod = types.ModuleType(stub)
+            if stub == "h5py":
+                mod.File = object
+            sys.modules[stub] = mod
+        sys.modules["lz4"].frame = sys.modules["lz4.frame"]
+        for k in ("filter", "core", "utils", "unified_index", "unified_builder"):
+            sys.modules.pop(k, None)
+        sys.path.insert(0, REFERENCE_DIR)
+        os.chdir(tmp)
+        out = {n: importlib.import_module(n) for n in names}
+        yield out
+    finally:
+        os.chdir(old_cwd)
+        sys.path[:] = old_path
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
