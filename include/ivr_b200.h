@@ -27,6 +27,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define IVR_API __attribute__((visibility("default")))
+#else
+#define IVR_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -49,11 +55,11 @@ extern "C" {
 typedef struct ivr_index ivr_index;
 
 /* ---- misc -------------------------------------------------------------- */
-const char* ivr_last_error(void);
-int         ivr_version(void);
-int         ivr_device_count(int* count);
+IVR_API const char* ivr_last_error(void);
+IVR_API int         ivr_version(void);
+IVR_API int         ivr_device_count(int* count);
 /* name / SM count / total bytes of a device (any pointer may be NULL) */
-int         ivr_device_info(int device, char* name, size_t name_len, int* sm_count,
+IVR_API int         ivr_device_info(int device, char* name, size_t name_len, int* sm_count,
                             int* cc_major, int* cc_minor, size_t* total_bytes);
 
 /* ---- flat inner-product index ------------------------------------------
@@ -62,15 +68,15 @@ int         ivr_device_info(int device, char* name, size_t name_len, int* sm_cou
  * Rows are stored row-major in HBM as bf16 (dim padded to a multiple of 64);
  * ids are the insertion order 0..ntotal-1.
  */
-int     ivr_index_create(int dim, int device, ivr_index** out);
-int     ivr_index_destroy(ivr_index* idx);
-int     ivr_index_reserve(ivr_index* idx, int64_t n_rows);           /* pre-size, avoids regrowth */
-int     ivr_index_add(ivr_index* idx, const float* x_host, int64_t n);
-int     ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* stream);
-int     ivr_index_reset(ivr_index* idx);
-int64_t ivr_index_ntotal(const ivr_index* idx);
-int     ivr_index_dim(const ivr_index* idx);
-int     ivr_index_device(const ivr_index* idx);
+IVR_API int     ivr_index_create(int dim, int device, ivr_index** out);
+IVR_API int     ivr_index_destroy(ivr_index* idx);
+IVR_API int     ivr_index_reserve(ivr_index* idx, int64_t n_rows);           /* pre-size, avoids regrowth */
+IVR_API int     ivr_index_add(ivr_index* idx, const float* x_host, int64_t n);
+IVR_API int     ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* stream);
+IVR_API int     ivr_index_reset(ivr_index* idx);
+IVR_API int64_t ivr_index_ntotal(const ivr_index* idx);
+IVR_API int     ivr_index_dim(const ivr_index* idx);
+IVR_API int     ivr_index_device(const ivr_index* idx);
 
 /* Replaces D, I = index.search(x, k)  (unified_index.py:503; core.py:891; system.py:1330).
  *   q      float32 [nq, dim] row-major
@@ -78,9 +84,9 @@ int     ivr_index_device(const ivr_index* idx);
  *   I      int64   [nq, k]   row ids + id_offset; -1 (score -FLT_MAX) where k > ntotal
  * id_offset lets a row shard report global ids (multi-GPU row sharding).
  */
-int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k,
+IVR_API int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k,
                      float* D_host, int64_t* I_host, int path);
-int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
+IVR_API int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
                             float* D_dev, int64_t* I_dev, int64_t id_offset, int path,
                             void* stream);
 
@@ -88,22 +94,22 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
  * the launching stream, only when enabled).  ms[0] = dominant scoring+select kernel,
  * ms[1] = top-k merge kernel(s), ms[2] = query preparation; launches[0..2] = launch
  * counts of the same.  Blocks until those events have completed. */
-int ivr_index_set_timing(ivr_index* idx, int enable);
-int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]);
+IVR_API int ivr_index_set_timing(ivr_index* idx, int enable);
+IVR_API int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]);
 /* which path the last search took (IVR_PATH_STREAM / IVR_PATH_MMA) */
-int ivr_index_last_path(const ivr_index* idx);
+IVR_API int ivr_index_last_path(const ivr_index* idx);
 
 /* K5: merge per-shard top-k lists after the all-gather
  * (semantic precedent: system.py:1721-1746 concat + sort + truncate).
  *   D_parts float32 [n_parts, nq, k], I_parts int64 [n_parts, nq, k] (device),
  *   entries with id < 0 are padding.  Output descending, ties -> lower id. */
-int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
+IVR_API int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
                           int64_t nq, int k, float* D_out, int64_t* I_out, void* stream);
 
 /* Replaces faiss.normalize_L2(x) (unified_index.py:1776): in-place row L2
  * normalisation, zero rows untouched. */
-int ivr_normalize_l2(int device, float* x_host, int64_t n, int d);
-int ivr_normalize_l2_device(int device, float* x_dev, int64_t n, int d, void* stream);
+IVR_API int ivr_normalize_l2(int device, float* x_host, int64_t n, int d);
+IVR_API int ivr_normalize_l2_device(int device, float* x_dev, int64_t n, int d, void* stream);
 
 /* ---- near-duplicate keyframe pruning ------------------------------------
  * All cosines follow sklearn's order of operations (normalise rows, then dot)
@@ -113,8 +119,8 @@ int ivr_normalize_l2_device(int device, float* x_dev, int64_t n, int d, void* st
 /* Replaces filter.calculate_similarities (filter.py:142-151) and the loop in
  * TemporalAnalyzer.detect_scene_boundaries (core.py:3612-3616):
  *   out[i-1] = cos(e[i-1], e[i]),  i = 1..n-1.   e: float32 [n, d]. */
-int ivr_consecutive_cosine(int device, const float* e_host, int64_t n, int d, float* out_host);
-int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int d,
+IVR_API int ivr_consecutive_cosine(int device, const float* e_host, int64_t n, int d, float* out_host);
+IVR_API int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int d,
                                   float* out_dev, void* stream);
 
 /* Replaces filter.filter_similar_frames_advanced applied per scene by
@@ -123,25 +129,25 @@ int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int
  * frame; drop frame i iff some ALREADY KEPT j in [i-min(window,len), i) has
  * cos(e_i, e_j) >= thr.  keep[i] = 1/0; frames outside every scene get 0.
  * Also writes cos_prev[i] = cos(e_i, e_{i-1}) (cos_prev[0] = 1) if non-NULL. */
-int ivr_dedup_window(int device, const float* e_host, int64_t n, int d,
+IVR_API int ivr_dedup_window(int device, const float* e_host, int64_t n, int d,
                      const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
                      int window, float thr, uint8_t* keep_host, float* cos_prev_host);
-int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, int d,
+IVR_API int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, int d,
                             const int64_t* scene_start_dev, const int64_t* scene_end_dev,
                             int64_t n_scenes, int window, float thr,
                             uint8_t* keep_dev, float* cos_prev_dev, uint32_t* mask_ws_dev,
                             void* stream);
 /* Timing of the last ivr_dedup_window_device call on this thread (events on the
  * launching stream): ms[0] = banded-cosine kernel, ms[1] = greedy resolve kernel. */
-int ivr_dedup_set_timing(int enable);
-int ivr_dedup_last_timing(float ms[2]);
+IVR_API int ivr_dedup_set_timing(int enable);
+IVR_API int ivr_dedup_last_timing(float ms[2]);
 
 /* Replaces filter.filter_similar_frames_in_scene (filter.py:178-222) when
  * force_last != 0, and the video_frame_filter.extract_unique_frames rule
  * (video_frame_filter.py:63-70) when force_last == 0 and min_distance == 1:
  * per scene keep frame 0; then keep i iff i - last_kept >= min_distance and
  * cos(e_i, e_last_kept) < thr; with force_last the scene's last frame is kept. */
-int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d,
+IVR_API int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d,
                     const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
                     int min_distance, float thr, int force_last, uint8_t* keep_host);
 

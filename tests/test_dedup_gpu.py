@@ -1,0 +1,137 @@
+"""GPU: near-duplicate pruning parity -- CUDA kernels vs. the reference's golden outputs
+(bit-exact keep lists on guard-banded fixtures) and vs. the oracle at larger sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dedup as od, synth  # noqa: E402
+
+CFG = dict(enable_similarity_filtering=True, similarity_threshold=0.95, min_frame_distance=1,
+           similarity_window_size=5, use_advanced_similarity_filtering=False)
+VARIANTS = {
+    "adv_w8_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=8),
+    "adv_w5_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=5),
+    "adv_w3_t090": dict(use_advanced_similarity_filtering=True, similarity_window_size=3,
+                        similarity_threshold=0.90),
+    "adv_w1_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=1),
+    "basic_m1_t095": dict(),
+    "basic_m2_t095": dict(min_frame_distance=2),
+    "basic_m1_t098": dict(similarity_threshold=0.98),
+    "disabled": dict(enable_similarity_filtering=False),
+}
+
+
+def cfg(**kw):
+    c = dict(CFG)
+    c.update(kw)
+    return c
+
+
+@pytest.mark.parametrize("name", ["dedup_d64", "dedup_d512"])
+def test_against_reference_golden(dedup_golden, name):
+    from ivr_b200 import frame_filter as ff
+    g = dedup_golden[name]
+    x = g["x"]
+    emb = [r for r in x]
+    n = len(emb)
+    sims = ff.calculate_similarities(emb)
+    assert len(sims) == n - 1
+    assert np.allclose(np.asarray(sims, np.float32), g["sims"], atol=2e-6)      # fp32, different sum order
+    for thr, tag in ((0.75, "t075"), (0.3, "t030")):
+        tp = ff.detect_scene_transitions(sims, thr)
+        assert tp == g[f"transitions_{tag}"].tolist()                           # guard band => exact
+    scenes = ff.group_into_scenes(ff.detect_scene_transitions(sims, 0.75), n, 2)
+    assert np.array_equal(np.asarray(scenes, np.int64).reshape(-1, 2), g["scenes_t075_m2"])
+    for tag, kw in VARIANTS.items():
+        fe, rows, stats = ff.apply_similarity_filtering_to_scenes(emb, list(range(n)), scenes, cfg(**kw))
+        assert rows == g[f"kept_{tag}"].tolist(), tag                           # bit-exact keep list
+        assert [stats["original"], stats["filtered"], stats["removed"]] == g[f"stats_{tag}"].tolist()
+        assert len(fe) == len(rows) and all(fe[i] is emb[r] for i, r in enumerate(rows))
+    whole = list(range(n))
+    assert ff.filter_similar_frames_advanced(emb, whole, cfg(**VARIANTS["adv_w8_t095"])) == g["kept_whole_adv_w8"].tolist()
+    assert ff.filter_similar_frames_in_scene(emb, whole, cfg()) == g["kept_whole_basic"].tolist()
+    emb_none = list(emb[:40])
+    for i in (0, 7, 8, 39):
+        emb_none[i] = None
+    s2 = ff.calculate_similarities(emb_none)
+    assert np.allclose(np.asarray(s2, np.float32), g["sims_none40"], atol=2e-6)
+    assert s2[0] == 1.0 and s2[6] == 1.0 and s2[7] == 1.0 and s2[8] == 1.0 and s2[38] == 1.0
+
+
+@pytest.mark.parametrize("n,d,w", [(20000, 512, 8), (5000, 768, 5), (3000, 100, 8), (4000, 384, 32),
+                                   (2000, 64, 1), (1000, 1024, 16)])
+def test_window_rule_vs_oracle_large(n, d, w):
+    from ivr_b200 import frame_filter as ff
+    x, _ = synth.dedup_frames_guarded(n, d, window=w, thresholds=(0.95, 0.75), seed=70 + w)
+    cosv = od.consecutive_cosines_fast(x)
+    scenes = od.scenes_from_cosines(cosv, n, 0.75, 2)
+    want = np.nonzero(od.window_keep_mask(x, scenes, w, 0.95))[0]
+    got = ff.FrameFilter(window=w, threshold=0.95).apply_filters(x)
+    assert np.array_equal(got, want)
+    sims = np.asarray(ff.calculate_similarities(x), np.float32)
+    assert np.allclose(sims, cosv, atol=3e-6)
+
+
+def test_chain_rules_vs_oracle():
+    from ivr_b200 import frame_filter as ff
+    x, _ = synth.dedup_frames_guarded(1500, 128, window=1, thresholds=(0.95, 0.98), seed=90)
+    emb = [r for r in x]
+    assert ff.extract_unique_frames_rule(emb, 0.98) == od.extract_unique_rule(emb, 0.98)
+    scenes = [(0, 99), (100, 100), (150, 1499)]
+    for md in (1, 2, 3):
+        c = cfg(min_frame_distance=md)
+        _, rows, _ = ff.apply_similarity_filtering_to_scenes(emb, list(range(1500)), scenes, c)
+        _, want, _ = od.apply_similarity_filtering_to_scenes(emb, list(range(1500)), scenes, c)
+        assert rows == want
+    feats = x[:400]
+    assert ff.detect_scene_boundaries(feats, 0.3, 5) == od.detect_scene_boundaries(feats, 0.3, 5)
+    assert ff.detect_scene_boundaries(feats[:8], 0.3, 5) == [(0, 7)]
+
+
+def test_edge_cases():
+    from ivr_b200 import frame_filter as ff
+    assert ff.calculate_similarities([]) == [] and ff.calculate_similarities([np.ones(4, np.float32)]) == []
+    one = [np.ones(8, np.float32)]
+    assert ff.filter_similar_frames_advanced(one, [5], cfg()) == [5]
+    assert ff.filter_similar_frames_in_scene(one, [5], cfg()) == [5]
+    assert ff.FrameFilter().apply_filters(np.zeros((0, 16), np.float32)).size == 0
+    z = np.zeros((6, 16), np.float32)                              # zero rows: cosine 0 (sklearn 0 -> 1 norm)
+    assert np.allclose(ff.calculate_similarities(z), 0.0)
+    same = np.tile(np.arange(1, 17, dtype=np.float32), (50, 1))    # identical frames: only frame 0 survives
+    assert ff.FrameFilter(window=8).apply_filters(same).tolist() == [0]
+    assert ff.filter_similar_frames_in_scene(list(same), list(range(50)), cfg()) == [0, 49]   # forced last
+    from ivr_b200 import _native as nat
+    with pytest.raises(nat.NativeError):
+        ff.filter_similar_frames_advanced(list(same), list(range(50)), cfg(similarity_window_size=40,
+                                                                          use_advanced_similarity_filtering=True))
+
+
+def test_config_b_property_1m_frames():
+    """BASELINE config B size (1M x 512, W=8, thr 0.95): size-independent properties --
+    (i) the result is identical when the input is processed as two halves split at a scene cut,
+    (ii) idempotence of the scene split, (iii) every dropped frame has a kept near-duplicate in
+    its window and no two kept frames within a window are near-duplicates (checked on a sample)."""
+    from ivr_b200 import frame_filter as ff
+    n, d, w, thr = 1_000_000, 512, 8, 0.95
+    rng = np.random.default_rng(123)
+    x = np.empty((n, d), np.float32)
+    for s in range(0, n, 100_000):
+        xs, _ = synth.dedup_frames(100_000, d, seed=1000 + s)
+        x[s:s + 100_000] = xs
+    f = ff.FrameFilter(window=w, threshold=thr)
+    kept = f.apply_filters(x)
+    st = dict(f.last_stats)
+    assert 0 < kept.size < n and np.all(np.diff(kept) > 0)
+    cut = 500_000                                               # synthetic chunks start new scenes here
+    k1 = ff.FrameFilter(window=w, threshold=thr).apply_filters(x[:cut])
+    k2 = ff.FrameFilter(window=w, threshold=thr).apply_filters(x[cut:]) + cut
+    assert np.array_equal(np.concatenate([k1, k2]), kept)
+    keep = np.zeros(n, bool)
+    keep[kept] = True
+    sims = np.asarray(ff.calculate_similarities(x[:20001]), np.float32)
+    scenes = od.scenes_from_cosines(sims, 20001, 0.75, 2)
+    want = od.window_keep_mask(x[:20001], scenes, w, thr)
+    last = scenes[-2][1] + 1                                     # the last scene may continue past the slice
+    assert np.array_equal(keep[:last], want[:last].astype(bool))
+    assert st["original"] >= kept.size and st["scenes"] > 1000

@@ -1,0 +1,129 @@
+"""CPU: the Python host wrappers (result semantics, metadata join, error behaviour) with the
+oracle injected as the index backend, checked against the golden outputs of the REFERENCE'S
+OWN wrappers.  (Injection is test-only; the product constructs the CUDA index.)"""
+import numpy as np
+import pytest
+
+from ivr_b200 import frame_filter as ff
+from ivr_b200.retriever import FAISSRetriever, KeyframeMetadata, SearchResult
+from ivr_b200.unified_builder import UnifiedBuilderIntegration, add_unified_index_support
+from ivr_b200.unified_index import UnifiedIndex, UnifiedIndexConfig
+from oracle import flat_ip
+
+
+def make_unified(sg):
+    index = flat_ip.IndexFlatIP(sg["xb"].shape[1])
+    chunk = sg["xb"].copy()
+    flat_ip.normalize_L2(chunk)
+    index.add(chunk)
+    u = UnifiedIndex()
+    u.faiss_index, u.metadata_list, u.is_loaded = index, sg["meta"], True
+    u.memory_maps = {"thumbnails": {}, "temporal": {}}
+    return u
+
+
+def rows_of(res):
+    return [[x["rank"], x["similarity_score"], x["index"], x["metadata"]["folder_name"],
+             x["metadata"]["frame_id"]] for x in res]
+
+
+def test_search_vectors_matches_reference(search_golden):
+    sg = search_golden
+    u = make_unified(sg)
+    for key, want in sg["results"]["search_vectors"].items():
+        if key == "k20_q0_even":
+            got = rows_of(u.search_vectors(sg["xq"][0], k=20, filter_func=lambda m: m["frame_id"] % 2 == 0))
+        else:
+            k, q = key.split("_")
+            got = rows_of(u.search_vectors(sg["xq"][int(q[1:])], k=int(k[1:])))
+        assert got == want, key
+    # 1 - ip: best hit has the LOWEST similarity_score; rank is 0-based
+    r = u.search_vectors(sg["xq"][0], k=10)
+    assert r[0]["rank"] == 0 and r[0]["similarity_score"] <= r[-1]["similarity_score"]
+
+
+def test_search_vectors_requires_loaded():
+    with pytest.raises(ValueError, match="Index not loaded"):
+        UnifiedIndex().search_vectors(np.zeros(4, np.float32))
+
+
+def test_search_unified_fast_matches_reference(search_golden):
+    sg = search_golden
+    b = UnifiedBuilderIntegration(system=None)
+    with pytest.raises(ValueError, match="Unified index not loaded"):
+        b.search_unified_fast(sg["xq"][1])
+    b.unified_index = make_unified(sg)
+    for key, want in sg["results"]["search_unified_fast"].items():
+        thr = float(key[3:])
+        res = b.search_unified_fast(sg["xq"][1], k=30, similarity_threshold=thr)
+        got = [[x["rank"], x["similarity_score"], x["index"], x["temporal_context"],
+                type(x["metadata"]).__name__, x["metadata"].folder_name, x["metadata"].frame_id] for x in res]
+        assert got == want, key
+
+    class Sys:
+        logger = None
+    s = Sys()
+    assert add_unified_index_support(s) is s.unified_builder
+    assert add_unified_index_support(s) is s.unified_builder
+
+
+def test_facade_tuple(search_golden):
+    sg = search_golden
+    u = make_unified(sg)
+    ids, scores, meta = u.search(sg["xq"], top_k=7)
+    assert ids.shape == (len(sg["xq"]), 7) and ids.dtype == np.int64 and scores.dtype == np.float32
+    assert np.all(np.diff(scores, axis=1) <= 0)
+    assert meta[0][0] is sg["meta"][int(ids[0, 0])]
+    ids2, scores2, meta2, ctx = u.augmented_search(sg["xq"][0], top_k=3)
+    assert ids2.shape == (1, 3) and ctx == [[[], [], []]]
+
+
+def test_faiss_retriever_matches_reference(search_golden, monkeypatch):
+    sg = search_golden
+    import ivr_b200.retriever as R
+    monkeypatch.setattr(R.faiss, "IndexFlatIP", lambda d, device=None: flat_ip.IndexFlatIP(d))
+    raw = (sg["xb"] * np.float32(2.5)).astype(np.float32)
+    kms = [KeyframeMetadata(folder_name=m["folder_name"], image_name=m["image_name"], frame_id=m["frame_id"],
+                            file_path=m["file_path"], clip_features=(raw[i] if i % 7 else None))
+           for i, m in enumerate(sg["meta"])]
+    fr = FAISSRetriever()
+    with pytest.raises(RuntimeError, match="Index not trained"):
+        fr.search(sg["xq"][0])
+    fr.build_index(raw, kms, validate_consistency=False)
+    assert fr.index.ntotal == sg["results"]["ntotal"]
+    out = fr.search(sg["xq"][:3] * np.float32(1.7), k=12)
+    got = [[r.metadata.folder_name, r.metadata.image_name, float(r.similarity_score), r.rank,
+            float(r.query_relevance)] for r in out]
+    want = sg["results"]["faiss_retriever_search"]
+    assert [g[:2] + g[3:4] for g in got] == [w[:2] + w[3:4] for w in want]         # ids + 1-based ranks, flattened
+    assert np.allclose([g[2] for g in got], [w[2] for w in want], atol=1e-6)
+    assert all(isinstance(r, SearchResult) for r in out)
+    out1 = fr.search(sg["xq"][4], k=5)
+    assert [[r.metadata.folder_name, r.metadata.image_name, r.rank] for r in out1] == \
+        [[w[0], w[1], w[3]] for w in sg["results"]["faiss_retriever_search_1d"]]
+    byid = sg["results"]["faiss_retriever_search_by_id"]
+    hits = fr.search_by_id(byid["key"], k=7)
+    assert [[r.metadata.folder_name, r.metadata.image_name, r.rank] for r in hits] == \
+        [[w[0], w[1], w[3]] for w in byid["hits"]]
+    assert fr.search_by_id("nope") == []
+    with pytest.raises(ValueError, match="Query dimension"):
+        fr.search(np.ones(5, np.float32))
+    with pytest.raises(ValueError, match="NaN"):
+        fr.search(np.full(sg["xb"].shape[1], np.nan, np.float32))
+    with pytest.raises(ValueError, match="Features count"):
+        fr.build_index(raw[:3], kms[:2])
+
+
+def test_scene_bookkeeping_matches_reference(dedup_golden):
+    g = dedup_golden["dedup_d64"]
+    sims = g["sims"]
+    n = len(g["x"])
+    for thr, tag in ((0.75, "t075"), (0.3, "t030")):
+        tp = ff.detect_scene_transitions(list(sims), thr)
+        assert tp == g[f"transitions_{tag}"].tolist()
+        for ml in (1, 2, 5):
+            assert np.array_equal(np.asarray(ff.group_into_scenes(tp, n, ml), np.int64).reshape(-1, 2),
+                                  g[f"scenes_{tag}_m{ml}"])
+    cfg = ff.create_config()
+    assert cfg["similarity_threshold"] == 0.95 and cfg["similarity_window_size"] == 5
+    assert UnifiedIndexConfig().thumbnail_size == (224, 224)

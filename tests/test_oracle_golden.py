@@ -1,0 +1,141 @@
+"""CPU: the oracle restatements against the golden vectors produced by the reference."""
+import numpy as np
+import pytest
+
+from oracle import comparator, dedup as od, flat_ip, synth
+
+CFG = dict(enable_similarity_filtering=True, similarity_threshold=0.95, min_frame_distance=1,
+           similarity_window_size=5, use_advanced_similarity_filtering=False)
+VARIANTS = {
+    "adv_w8_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=8),
+    "adv_w5_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=5),
+    "adv_w3_t090": dict(use_advanced_similarity_filtering=True, similarity_window_size=3,
+                        similarity_threshold=0.90),
+    "adv_w1_t095": dict(use_advanced_similarity_filtering=True, similarity_window_size=1),
+    "basic_m1_t095": dict(),
+    "basic_m2_t095": dict(min_frame_distance=2),
+    "basic_m1_t098": dict(similarity_threshold=0.98),
+    "disabled": dict(enable_similarity_filtering=False),
+}
+
+
+def cfg(**kw):
+    c = dict(CFG)
+    c.update(kw)
+    return c
+
+
+@pytest.mark.parametrize("name", ["dedup_d64", "dedup_d512"])
+def test_dedup_oracle_matches_reference(dedup_golden, name):
+    g = dedup_golden[name]
+    x = g["x"]
+    emb = [r for r in x]
+    n = len(emb)
+    sims = od.calculate_similarities(emb)
+    assert np.array_equal(np.asarray(sims, np.float32), g["sims"])          # bit-exact
+    for thr, tag in ((0.75, "t075"), (0.3, "t030")):
+        tp = od.detect_scene_transitions(sims, thr)
+        assert np.array_equal(np.asarray(tp, np.int64), g[f"transitions_{tag}"])
+        for ml in (1, 2, 5):
+            sc = od.group_into_scenes(tp, n, ml)
+            assert np.array_equal(np.asarray(sc, np.int64).reshape(-1, 2), g[f"scenes_{tag}_m{ml}"])
+    scenes = od.group_into_scenes(od.detect_scene_transitions(sims, 0.75), n, 2)
+    for tag, kw in VARIANTS.items():
+        _, rows, stats = od.apply_similarity_filtering_to_scenes(emb, list(range(n)), scenes, cfg(**kw))
+        assert np.array_equal(np.asarray(rows, np.int64), g[f"kept_{tag}"]), tag
+        assert [stats["original"], stats["filtered"], stats["removed"]] == g[f"stats_{tag}"].tolist()
+    whole = list(range(n))
+    assert od.filter_similar_frames_advanced(emb, whole, cfg(**VARIANTS["adv_w8_t095"])) == g["kept_whole_adv_w8"].tolist()
+    assert od.filter_similar_frames_in_scene(emb, whole, cfg()) == g["kept_whole_basic"].tolist()
+    emb_none = list(emb[:40])
+    for i in (0, 7, 8, 39):
+        emb_none[i] = None
+    assert np.array_equal(np.asarray(od.calculate_similarities(emb_none), np.float32), g["sims_none40"])
+
+
+@pytest.mark.parametrize("name", ["dedup_d64", "dedup_d512"])
+def test_dedup_vectorised_oracle_matches_reference(dedup_golden, name):
+    """The fast (vectorised) oracle used at large sizes agrees with the reference outputs."""
+    g = dedup_golden[name]
+    x = g["x"]
+    n = len(x)
+    cosv = od.consecutive_cosines_fast(x)
+    assert np.allclose(cosv, g["sims"], atol=2e-6)
+    scenes = od.scenes_from_cosines(cosv, n, 0.75, 2)
+    assert np.array_equal(np.asarray(scenes, np.int64).reshape(-1, 2), g["scenes_t075_m2"])
+    for tag, w, thr in (("adv_w8_t095", 8, 0.95), ("adv_w5_t095", 5, 0.95), ("adv_w3_t090", 3, 0.90),
+                        ("adv_w1_t095", 1, 0.95)):
+        keep = od.window_keep_mask(x, scenes, w, thr)
+        assert np.array_equal(np.nonzero(keep)[0], g[f"kept_{tag}"]), tag
+    assert od.guard_band_ok(x, 8, (0.95, 0.75, 0.98, 0.9, 0.3))
+
+
+def test_flat_ip_against_torch_topk():
+    import torch
+    xb = synth.clip_like(5000, 64, seed=1, n_centres=64)
+    xq = synth.clip_like(17, 64, seed=2, n_centres=64)
+    idx = flat_ip.IndexFlatIP(64)
+    idx.add(xb[:3000])
+    idx.add(xb[3000:])
+    assert idx.ntotal == 5000
+    D, I = idx.search(xq, 100, db_block=1024)                       # exercises the running merge
+    tv, ti = torch.topk(torch.from_numpy(xq) @ torch.from_numpy(xb).T, 100, dim=1)
+    assert not comparator.compare_topk(D, I, tv.numpy(), ti.numpy(), lambda ids: idx.scores_of(xq, ids), tol=1e-5)
+    assert np.all(np.diff(D, axis=1) <= 0)
+
+
+def test_flat_ip_padding_and_ties():
+    idx = flat_ip.IndexFlatIP(8)
+    D, I = idx.search(np.ones((2, 8), np.float32), 3)
+    assert (I == -1).all() and (D == flat_ip.NEG_PAD).all()
+    x = np.zeros((5, 8), np.float32)
+    x[:, 0] = [1, 2, 2, 2, 0]
+    idx.add(x)
+    D, I = idx.search(np.eye(1, 8, dtype=np.float32), 7)
+    assert I[0].tolist() == [1, 2, 3, 0, 4, -1, -1]                  # ties -> lower id first
+    assert D[0, 5] == flat_ip.NEG_PAD
+    D2, I2 = idx.search(np.eye(1, 8, dtype=np.float32), 2)
+    assert I2[0].tolist() == [1, 2]
+
+
+def test_normalize_l2_contract():
+    x = np.array([[3, 4, 0], [0, 0, 0], [1, 1, 1]], np.float32)
+    flat_ip.normalize_L2(x)
+    assert np.allclose(x[0], [0.6, 0.8, 0]) and not x[1].any()
+    assert np.allclose(np.linalg.norm(x[2]), 1, atol=1e-6)
+    with pytest.raises(ValueError):
+        flat_ip.normalize_and_validate(np.array([np.nan, 1.0]))
+
+
+def test_merge_shard_results_oracle():
+    xb = synth.gaussian_unit(3000, 32, seed=3)
+    xq = synth.gaussian_unit(5, 32, seed=4)
+    full = flat_ip.IndexFlatIP(32)
+    full.add(xb)
+    D, I = full.search(xq, 50)
+    Ds, Is = [], []
+    for a, b in ((0, 700), (700, 2900), (2900, 3000)):
+        s = flat_ip.IndexFlatIP(32)
+        s.add(xb[a:b])
+        d, i = s.search(xq, 50)
+        Ds.append(d)
+        Is.append(np.where(i >= 0, i + a, -1))
+    Dm, Im = flat_ip.merge_shard_results(Ds, Is, 50)
+    # BLAS blocks differently for different shard shapes -> last-ulp score differences are expected
+    assert np.array_equal(Im, I) and np.allclose(Dm, D, atol=1e-6)
+
+
+def test_comparator_flags_real_errors():
+    xb = synth.clip_like(2000, 32, seed=5, n_centres=16)
+    xq = synth.clip_like(3, 32, seed=6, n_centres=16)
+    idx = flat_ip.IndexFlatIP(32)
+    idx.add(xb)
+    D, I = idx.search(xq, 20)
+    so = lambda ids: idx.scores_of(xq, ids)
+    assert comparator.compare_topk(D, I, D, I, so) == []
+    Ibad = I.copy()
+    Ibad[0, 0] = int(np.argmin(xb @ xq[0]))                          # clearly not a top hit
+    assert comparator.compare_topk(D, Ibad, D, I, so)
+    Dbad = D.copy()
+    Dbad[1, 3] += 0.01
+    assert comparator.compare_topk(Dbad, I, D, I, so)

@@ -1,0 +1,233 @@
+"""GPU: exact top-k search parity -- CUDA path (through the C ABI) vs. the oracle.
+
+Tolerance (north_star): identical ids except ties within 1e-3 of the k-th score; scores
+within 1e-3 (rows are stored as bf16, accumulation is fp32).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import comparator, flat_ip, synth  # noqa: E402
+
+TOL = 1e-3
+
+
+def build(xb, chunk=None):
+    import ivr_b200
+    idx = ivr_b200.IndexFlatIP(xb.shape[1])
+    ref = flat_ip.IndexFlatIP(xb.shape[1])
+    if chunk is None:
+        idx.add(xb)
+    else:                                          # ragged multi-chunk add (regrowth path)
+        for s in range(0, len(xb), chunk):
+            idx.add(xb[s:s + chunk])
+    ref.add(xb)
+    assert idx.ntotal == ref.ntotal == len(xb)
+    return idx, ref
+
+
+def check(idx, ref, xq, k, path=0, tol=TOL):
+    idx.search_path = path
+    D, I = idx.search(xq, k)
+    Dr, Ir = ref.search(xq, k)
+    bad = comparator.compare_topk(D, I, Dr, Ir, lambda ids: ref.scores_of(xq, ids), tol)
+    assert not bad, "\n".join(bad[:10])
+    return D, I
+
+
+@pytest.mark.parametrize("d", [512, 768, 384, 100, 64, 1024])
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 7])
+def test_stream_path_dims_and_batches(d, nq):
+    xb = synth.clip_like(20000, d, seed=31, n_centres=256)
+    xq = synth.clip_like(nq, d, seed=32, n_centres=256)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=1)
+    assert idx.last_timing()["path"] == "stream"
+
+
+@pytest.mark.parametrize("k", [1, 5, 50, 100, 128, 129, 300, 1000, 1024])
+def test_stream_path_k_values(k):
+    xb = synth.clip_like(30000, 128, seed=33, n_centres=64)
+    xq = synth.clip_like(3, 128, seed=34, n_centres=64)
+    idx, ref = build(xb, chunk=7001)
+    check(idx, ref, xq, k, path=1)
+
+
+def test_config_a_100k_x512_k100_stream():
+    """BASELINE config A shape (100k x 512, k=100), a slice of the 1k queries on the K3 path."""
+    xb = synth.clip_like(100_000, 512, seed=1234 + 1)
+    xq = synth.clip_like(16, 512, seed=4321)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=1)
+
+
+def test_adversarial_ties_gaussian():
+    xb = synth.gaussian_unit(50_000, 512, seed=0)
+    xq = synth.gaussian_unit(4, 512, seed=1)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=1)
+
+
+def test_small_and_empty_indexes():
+    import ivr_b200
+    idx = ivr_b200.IndexFlatIP(64)
+    xq = synth.gaussian_unit(3, 64, seed=2)
+    D, I = idx.search(xq, 5)                                   # empty index: all padding
+    assert (I == -1).all() and (D == flat_ip.NEG_PAD).all()
+    for n in (1, 3, 99, 100, 101, 257):
+        xb = synth.gaussian_unit(n, 64, seed=3 + n)
+        idx, ref = build(xb)
+        D, I = check(idx, ref, xq, 100, path=1)
+        if n < 100:
+            assert (I[:, n:] == -1).all() and (D[:, n:] == flat_ip.NEG_PAD).all()
+    D0, I0 = idx.search(np.zeros((0, 64), np.float32), 5)
+    assert D0.shape == (0, 5) and I0.shape == (0, 5)
+
+
+def test_duplicates_and_exact_ties():
+    base = synth.gaussian_unit(50, 64, seed=9)
+    xb = np.concatenate([base] * 40)                           # every row appears 40x -> massive exact ties
+    xq = base[:3]
+    idx, ref = build(xb)
+    D, I = check(idx, ref, xq, 100, path=1)
+    assert np.all(np.abs(D[:, :40] - 1.0) < 5e-3)
+
+
+def test_reset_and_readd():
+    xb = synth.clip_like(5000, 64, seed=40, n_centres=32)
+    xq = synth.clip_like(2, 64, seed=41, n_centres=32)
+    idx, ref = build(xb)
+    idx.reset()
+    assert idx.ntotal == 0
+    idx.add(xb[:1234])
+    ref2 = flat_ip.IndexFlatIP(64)
+    ref2.add(xb[:1234])
+    check(idx, ref2, xq, 10, path=1)
+
+
+def test_errors():
+    import ivr_b200
+    from ivr_b200 import _native as nat
+    idx = ivr_b200.IndexFlatIP(32)
+    idx.add(synth.gaussian_unit(10, 32, seed=1))
+    with pytest.raises(ValueError):
+        idx.search(np.ones((1, 31), np.float32), 5)            # dimension mismatch
+    with pytest.raises(ValueError):
+        idx.add(np.ones((4, 33), np.float32))
+    with pytest.raises(ValueError):
+        idx.search(np.ones((1, 32), np.float32), 0)
+    with pytest.raises(nat.NativeError) as e:
+        idx.search(np.ones((1, 32), np.float32), nat.IVR_MAX_K + 1)
+    assert e.value.code == nat.IVR_EUNSUPPORTED
+
+
+def test_normalize_l2_matches_oracle():
+    import ivr_b200
+    x = (synth.gaussian_unit(1000, 100, seed=5) * 3.7).astype(np.float32)
+    x[17] = 0
+    want = x.copy()
+    flat_ip.normalize_L2(want)
+    ivr_b200.normalize_L2(x)
+    assert np.allclose(x, want, atol=1e-6) and not x[17].any()
+
+
+def test_device_tensor_search_and_id_offset():
+    import torch
+    import ivr_b200
+    xb = synth.clip_like(8000, 512, seed=50, n_centres=64)
+    xq = synth.clip_like(3, 512, seed=51, n_centres=64)
+    idx = ivr_b200.IndexFlatIP(512)
+    idx.add(torch.from_numpy(xb).cuda())                       # device-side add
+    ref = flat_ip.IndexFlatIP(512)
+    ref.add(xb)
+    D, I = idx.search_tensor(torch.from_numpy(xq).cuda(), 20, id_offset=1_000_000_000_000)
+    torch.cuda.synchronize()
+    Dr, Ir = ref.search(xq, 20)
+    bad = comparator.compare_topk(D.cpu().numpy(), I.cpu().numpy() - 1_000_000_000_000, Dr, Ir,
+                                  lambda ids: ref.scores_of(xq, ids), TOL)
+    assert not bad, bad
+
+
+def test_topk_merge_kernel_matches_oracle():
+    import ctypes
+    import torch
+    from ivr_b200 import _native as nat
+    rng = np.random.default_rng(0)
+    for n_parts, nq, k in ((8, 33, 100), (2, 5, 7), (130, 3, 20), (3, 4, 1000)):
+        D = np.sort(rng.standard_normal((n_parts, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+        I = np.stack([rng.permutation(10 * k * n_parts)[:nq * k].reshape(nq, k) + p * 10_000_000
+                      for p in range(n_parts)]).astype(np.int64)
+        I[0, 0, k // 2:] = -1                                   # a short (padded) shard list
+        D[0, 0, k // 2:] = flat_ip.NEG_PAD
+        D[1 % n_parts, 1 % nq, 0] = D[0, 1 % nq, 0]             # an exact cross-shard tie
+        Dm, Im = flat_ip.merge_shard_results(list(D), list(I), k)
+        Dd, Id = torch.from_numpy(D).cuda(), torch.from_numpy(I).cuda()
+        Do = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        Io = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        nat.check(nat.lib.ivr_topk_merge_device(0, Dd.data_ptr(), Id.data_ptr(), n_parts, nq, k,
+                                                Do.data_ptr(), Io.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(Io.cpu().numpy(), Im), (n_parts, nq, k)   # integer/bit exact
+        assert np.array_equal(Do.cpu().numpy(), Dm)
+
+
+def test_wrappers_against_reference_golden(search_golden):
+    """The reference's own wrapper outputs (golden) vs. our wrappers on the CUDA index."""
+    import ivr_b200
+    sg = search_golden
+    u = ivr_b200.UnifiedIndex()
+    u.build_from_embeddings(sg["xb"], sg["meta"])
+    ref = flat_ip.IndexFlatIP(sg["xb"].shape[1])
+    ref.add(sg["xb"])
+    for key, want in sg["results"]["search_vectors"].items():
+        if key == "k20_q0_even":
+            continue
+        k, q = key.split("_")
+        k, qi = int(k[1:]), int(q[1:])
+        got = u.search_vectors(sg["xq"][qi], k=k)
+        assert len(got) == len(want)
+        assert [g["rank"] for g in got] == [w[0] for w in want]           # 0-based, dense
+        D = np.array([[1.0 - g["similarity_score"] for g in got]], np.float32)
+        I = np.array([[g["index"] for g in got]], np.int64)
+        Dr = np.array([[1.0 - w[1] for w in want]], np.float32)
+        Ir = np.array([[w[2] for w in want]], np.int64)
+        bad = comparator.compare_topk(D, I, Dr, Ir, lambda ids: ref.scores_of(sg["xq"][qi:qi + 1], ids), TOL)
+        assert not bad, (key, bad)
+        for g in got:
+            assert g["metadata"] is sg["meta"][g["index"]]
+    b = ivr_b200.UnifiedBuilderIntegration(system=None)
+    b.unified_index = u
+    for key, want in sg["results"]["search_unified_fast"].items():
+        got = b.search_unified_fast(sg["xq"][1], k=30, similarity_threshold=float(key[3:]))
+        assert abs(len(got) - len(want)) <= 1                               # threshold on 1-ip, 1e-3 band
+        for g in got:
+            assert g["similarity_score"] >= float(key[3:]) and g["temporal_context"] == []
+            assert type(g["metadata"]).__name__ == "KeyframeMetadata"
+    ids, scores, meta = ivr_b200.RAGBuilder().build_index(sg["xb"], sg["meta"]).search(sg["xq"], top_k=5)
+    assert ids.shape == (len(sg["xq"]), 5) and np.all(np.diff(scores, axis=1) <= 0)
+
+
+def test_faiss_retriever_on_gpu(search_golden):
+    import ivr_b200
+    sg = search_golden
+    raw = (sg["xb"] * np.float32(2.5)).astype(np.float32)
+    kms = [ivr_b200.KeyframeMetadata(folder_name=m["folder_name"], image_name=m["image_name"],
+                                     frame_id=m["frame_id"], file_path=m["file_path"],
+                                     clip_features=(raw[i] if i % 7 else None))
+           for i, m in enumerate(sg["meta"])]
+    fr = ivr_b200.FAISSRetriever()
+    fr.build_index(raw, kms, validate_consistency=False)
+    out = fr.search(sg["xq"][:3] * np.float32(1.7), k=12)
+    want = sg["results"]["faiss_retriever_search"]
+    assert len(out) == len(want) == 36
+    assert [r.rank for r in out] == [w[3] for w in want]
+    # same hit SETS per query (order inside a 1e-3 band may differ), identical re-scored cosines
+    for q in range(3):
+        g = {(r.metadata.folder_name, r.metadata.image_name): r.similarity_score for r in out[q * 12:(q + 1) * 12]}
+        w = {(x[0], x[1]): x[2] for x in want[q * 12:(q + 1) * 12]}
+        common = set(g) & set(w)
+        assert len(common) >= 11
+        for key in common:
+            assert abs(g[key] - w[key]) < 1e-6
