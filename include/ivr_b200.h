@@ -13,8 +13,9 @@
  *   - every function returns 0 (IVR_OK) or a negative IVR_E* code; a
  *     thread-local message is available from ivr_last_error().
  *   - "*_device" variants take DEVICE pointers on the handle's GPU and a
- *     cudaStream_t (as void*; NULL = the handle's own stream) and never block
- *     the host; the plain variants take HOST pointers, do the H2D/D2H copies
+ *     cudaStream_t (as void*; NULL = the legacy default stream, exactly as in
+ *     the CUDA runtime) and never block the host; the plain variants take HOST
+ *     pointers, run on a stream owned by the handle, do the H2D/D2H copies
  *     themselves and return when the outputs are written.
  *   - there is NO CPU fallback: without a CUDA device every compute call
  *     fails with IVR_ENODEVICE.

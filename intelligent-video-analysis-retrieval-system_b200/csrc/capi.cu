@@ -116,6 +116,7 @@ int ivr_index_create(int dim, int device, ivr_index** out) {
     cudaError_t e = cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&idx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->rows_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error("index_create: %s", cudaGetErrorString(e));
         delete idx;
@@ -134,6 +135,7 @@ int ivr_index_destroy(ivr_index* idx) {
     if (idx->io) cudaFree(idx->io);
     if (idx->pin) cudaFreeHost(idx->pin);
     for (auto& ev : idx->ev) if (ev) cudaEventDestroy(ev);
+    if (idx->rows_ready) cudaEventDestroy(idx->rows_ready);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
     return IVR_OK;
@@ -150,10 +152,12 @@ int ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* st
     if (!idx || n < 0 || (n > 0 && !x_dev)) { set_error("add_device: bad argument"); return IVR_EINVAL; }
     if (n == 0) return IVR_OK;
     IVR_CUDA(cudaSetDevice(idx->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : idx->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);       // NULL = the legacy default stream, as in CUDA
     if (idx->ntotal + n > 0x7fffffff) { set_error("a shard holds at most 2^31-1 rows"); return IVR_EUNSUPPORTED; }
     IVR_TRY(ensure_capacity(idx, idx->ntotal + n, st));
     IVR_TRY(convert_rows(idx, x_dev, n, idx->ntotal, st));
+    IVR_CUDA(cudaEventRecord(idx->rows_ready, st));
+    idx->rows_ready_set = true;
     idx->ntotal += n;
     return IVR_OK;
 }
@@ -222,7 +226,8 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
     if (k > IVR_MAX_K) { set_error("search: k=%d exceeds IVR_MAX_K=%d", k, IVR_MAX_K); return IVR_EUNSUPPORTED; }
     if (nq == 0) return IVR_OK;
     IVR_CUDA(cudaSetDevice(idx->device));
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : idx->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);       // NULL = the legacy default stream, as in CUDA
+    if (idx->rows_ready_set) IVR_CUDA(cudaStreamWaitEvent(st, idx->rows_ready, 0));   // rows added on another stream
     idx->launches[0] = idx->launches[1] = idx->launches[2] = 0;
     idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = false;
     if (idx->ntotal == 0) {

@@ -28,6 +28,11 @@ struct ivr_index {
     alignas(64) unsigned char tmap_rows[128];
     const void* tmap_rows_base = nullptr;
     int64_t     tmap_rows_n    = -1;
+    int         tmap_rows_box  = 0;
+
+    // recorded after every device-side add on its stream; searches on other streams wait on it
+    cudaEvent_t rows_ready = nullptr;
+    bool        rows_ready_set = false;
 
     // timing of the last device search
     bool        timing = false;

@@ -98,8 +98,11 @@ def test_edge_cases():
     assert ff.FrameFilter().apply_filters(np.zeros((0, 16), np.float32)).size == 0
     z = np.zeros((6, 16), np.float32)                              # zero rows: cosine 0 (sklearn 0 -> 1 norm)
     assert np.allclose(ff.calculate_similarities(z), 0.0)
-    same = np.tile(np.arange(1, 17, dtype=np.float32), (50, 1))    # identical frames: only frame 0 survives
-    assert ff.FrameFilter(window=8).apply_filters(same).tolist() == [0]
+    same = np.tile(np.arange(1, 17, dtype=np.float32), (50, 1))    # identical frames: a frame survives only
+    # when no KEPT frame lies within the window: 0, 9, 18, ... for W=8 (the reference rule, filter.py:241-251)
+    assert ff.FrameFilter(window=8).apply_filters(same).tolist() == [0, 9, 18, 27, 36, 45]
+    assert ff.FrameFilter(window=8).apply_filters(same).tolist() == \
+        od.filter_similar_frames_advanced(list(same), list(range(50)), cfg(similarity_window_size=8))
     assert ff.filter_similar_frames_in_scene(list(same), list(range(50)), cfg()) == [0, 49]   # forced last
     from ivr_b200 import _native as nat
     with pytest.raises(nat.NativeError):

@@ -54,6 +54,69 @@ def test_stream_path_k_values(k):
     check(idx, ref, xq, k, path=1)
 
 
+@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_group2"])
+def cta_group(request, monkeypatch):
+    monkeypatch.setenv("IVR_MMA_CTA_GROUP", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("d", [512, 384, 64, 100])
+@pytest.mark.parametrize("nq", [5, 128, 300])
+def test_mma_path_dims_and_batches(d, nq, cta_group):
+    xb = synth.clip_like(30000, d, seed=61, n_centres=256)
+    xq = synth.clip_like(nq, d, seed=62, n_centres=256)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=2)
+    assert idx.last_timing()["path"] == "mma"
+
+
+@pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 1000, 5000])
+def test_mma_path_small_indexes(n, cta_group):
+    xb = synth.gaussian_unit(n, 128, seed=63 + n)
+    xq = synth.gaussian_unit(37, 128, seed=64)
+    idx, ref = build(xb)
+    D, I = check(idx, ref, xq, 100, path=2)
+    if n < 100:
+        assert (I[:, n:] == -1).all()
+
+
+@pytest.mark.parametrize("k", [1, 10, 128, 129, 300, 1000])
+def test_mma_path_k_values(k, cta_group):
+    xb = synth.clip_like(40000, 128, seed=65, n_centres=64)
+    xq = synth.clip_like(200, 128, seed=66, n_centres=64)
+    idx, ref = build(xb)
+    check(idx, ref, xq, k, path=2)
+
+
+def test_config_a_100k_x512_1k_queries_k100(cta_group):
+    """BASELINE config A in full: 100k x 512, 1000 queries, k=100 (batched tcgen05 path)."""
+    xb = synth.clip_like(100_000, 512, seed=1234 + 1)
+    xq = synth.clip_like(1000, 512, seed=4321)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=0)
+    assert idx.last_timing()["path"] == "mma"
+
+
+def test_mma_adversarial_ties_and_duplicates(cta_group):
+    xb = synth.gaussian_unit(60_000, 512, seed=0)
+    xq = synth.gaussian_unit(150, 512, seed=1)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=2)
+    base = synth.gaussian_unit(50, 64, seed=9)
+    xb = np.concatenate([base] * 40)
+    idx, ref = build(xb)
+    check(idx, ref, base[:20], 100, path=2)
+
+
+def test_mma_and_stream_paths_agree():
+    xb = synth.clip_like(50_000, 512, seed=67, n_centres=128)
+    xq = synth.clip_like(8, 512, seed=68, n_centres=128)
+    idx, ref = build(xb)
+    D1, I1 = check(idx, ref, xq, 50, path=1)
+    D2, I2 = check(idx, ref, xq, 50, path=2)
+    assert np.abs(D1 - D2).max() < 1e-3
+
+
 def test_config_a_100k_x512_k100_stream():
     """BASELINE config A shape (100k x 512, k=100), a slice of the 1k queries on the K3 path."""
     xb = synth.clip_like(100_000, 512, seed=1234 + 1)
