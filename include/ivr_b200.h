@@ -45,7 +45,7 @@ extern "C" {
 #define IVR_ENOMEM     -4   /* device or pinned-host allocation failed                     */
 #define IVR_EUNSUPPORTED -5 /* argument outside the supported range (e.g. k > IVR_MAX_K)   */
 
-#define IVR_MAX_K       1024  /* reference caps SearchOptions.limit at 1000 (system.py:83-92) */
+#define IVR_MAX_K       2048  /* reference caps SearchOptions.limit at 1000 (system.py:83-92) */
 #define IVR_MAX_WINDOW  32    /* dedup look-back window (reference default 5, config B uses 8) */
 
 /* search path selector for ivr_index_search*(): */

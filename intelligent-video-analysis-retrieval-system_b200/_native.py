@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libivr_b200.so")
 
 IVR_OK, IVR_EINVAL, IVR_ENODEVICE, IVR_ECUDA, IVR_ENOMEM, IVR_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-IVR_MAX_K = 1024
+IVR_MAX_K = 2048
 IVR_MAX_WINDOW = 32
 PATH_AUTO, PATH_STREAM, PATH_MMA = 0, 1, 2
 

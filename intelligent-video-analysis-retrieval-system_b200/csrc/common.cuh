@@ -7,7 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -37,7 +37,7 @@ void set_error(const char* fmt, ...);   // capi.cu (thread-local message)
         if (_r != IVR_OK) return _r;   \
     } while (0)
 
-constexpr int kDimAlign = 64;          // rows are padded to a multiple of 64 bf16 (one 128B swizzle atom)
+constexpr int kDimAlign = 64;          // rows are padded to a multiple of 64 fp16 (one 128B swizzle atom)
 inline int pad_dim(int d) { return (d + kDimAlign - 1) / kDimAlign * kDimAlign; }
 
 // list capacity (entries) used by the streaming selectors for a given k:
@@ -73,9 +73,10 @@ __device__ __forceinline__ float4 ldg_nc_f4(const void* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-// two packed bf16 -> two fp32 (exact)
-__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+// two packed fp16 -> two fp32 (exact)
+__device__ __forceinline__ float2 h2f2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
 
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }

@@ -1,4 +1,4 @@
-// index.cuh -- the flat inner-product index handle (device-resident bf16 rows).
+// index.cuh -- the flat inner-product index handle (device-resident fp16 rows).
 #pragma once
 
 #include "common.cuh"
@@ -10,7 +10,7 @@ struct ivr_index {
     int      sm_count = 0;
     int64_t  ntotal   = 0;
     int64_t  capacity = 0;        // rows allocated
-    __nv_bfloat16* rows = nullptr;   // [capacity, dpad] row-major, HBM
+    __half* rows = nullptr;          // [capacity, dpad] row-major fp16, HBM
 
     cudaStream_t stream = nullptr;   // handle-owned stream for the host-pointer entry points
 
@@ -67,10 +67,11 @@ struct MergeIn {
     int     n_lists;
     int     fixed_count;
 };
-// final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset
+// final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset;
+// scores are multiplied by q_scale[q] when q_scale != nullptr (power-of-two query scaling)
 int merge_lists_final(const MergeIn& in, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                       int64_t id_offset, uint64_t* tmp_entries, int* tmp_counts,
-                      cudaStream_t st, int* n_launches);
+                      cudaStream_t st, int* n_launches, const float* q_scale = nullptr);
 size_t merge_tmp_entries(int n_lists, int64_t nq, int k);   // #keys of scratch the merge may need
 
 }  // namespace ivr

@@ -3,23 +3,31 @@
 // Replaces D, I = index.search(x, k) for query batches (unified_index.py:503 is
 // called once per query by the reference; core.py:891 already passes [nq, d]).
 //
-//   S[q, r] = <Q[q,:], X[r,:]>      Q: [nq, dpad] bf16 (converted per call)
-//                                   X: [ntotal, dpad] bf16 rows, HBM resident
+//   S[q, r] = <Q[q,:], X[r,:]>      Q: [nq, dpad] fp16 (converted + pow2-scaled per call)
+//                                   X: [ntotal, dpad] fp16 rows, HBM resident
 //
 // One persistent CTA per SM (CG = 1) or one CTA pair per TPC (CG = 2,
-// tcgen05 cta_group::2).  A work unit is a (128*CG queries) x (256 rows) tile:
-//   * the query tile stays RESIDENT in shared memory (dpad <= 512: 128 x dpad bf16
+// tcgen05 cta_group::2).  A work unit is a (128*CG queries) x (256 rows) tile.
+//   * SCHEDULE.  The row tiles are cut into PHASES whose rows fit in L2 (default 48 MB).
+//     Inside a phase the (query tile, row tile) units are linearised query-tile-major and
+//     split into equal contiguous ranges, one per CTA group, the same split in every phase:
+//     a group works on the same <= 2-3 query tiles for the whole kernel, every group has
+//     the same MMA work, and each row is fetched from HBM once per search (the other
+//     query tiles hit it in L2).
+//   * the query tile stays RESIDENT in shared memory (dpad <= 512: 128 x dpad fp16
 //     = 128 KB) -- only the row tiles stream through a TMA/mbarrier ring, which
 //     halves the L2->SMEM traffic of a classic GEMM tile loop;
 //   * warp 0 (one lane) issues TMA loads (cp.async.bulk.tensor, SWIZZLE_128B);
-//   * warp 1 (one lane) issues tcgen05.mma kind::f16 (bf16 x bf16 -> fp32) into one
+//   * warp 1 (one lane) issues tcgen05.mma kind::f16 (fp16 x fp16 -> fp32) into one
 //     of two 256-column TMEM accumulators;
-//   * warps 4-7 drain the other accumulator with tcgen05.ld (32 lanes x 32 columns
-//     per instruction): each THREAD owns one query, compares its 256 scores against
-//     that query's running admission threshold in registers and appends the few
-//     survivors to the query's candidate list; full lists are compacted by a warp
-//     bitonic sort.  The score matrix never reaches shared or global memory.
-// The per-(CTA, query-tile) survivors are folded by topk_merge.cu.
+//   * warps 4-11 are two epilogue sets, one per accumulator: tcgen05.ld hands every
+//     THREAD one query's 32 scores per instruction; the thread compares them with that
+//     query's admission threshold (register; the max of its own k-th best and a
+//     per-query threshold shared by all CTAs through global memory), a warp vote skips
+//     chunks without survivors, survivors are appended branch-free (predicated stores)
+//     to the query's candidate list; full lists are compacted by a warp bitonic sort.
+//     The score matrix never reaches shared or global memory.
+// The per-(CTA, query-tile, set) survivors are folded by topk_merge.cu.
 //
 // Algorithmic work: 2 * ntotal * dpad * nq FLOP per search.
 #include "index.cuh"
@@ -30,10 +38,10 @@
 
 namespace ivr {
 
-constexpr int kMmaThreads   = 256;
+constexpr int kMmaThreads   = 384;                 // 4 control warps + 2 epilogue sets of 4 warps
 constexpr int kTileN        = 256;                 // DB rows per tile (UMMA N)
 constexpr int kTileQ        = 128;                 // queries per CTA (UMMA M per CTA)
-constexpr int kKBlock       = 64;                  // bf16 per 128-byte swizzle row
+constexpr int kKBlock       = 64;                  // fp16 per 128-byte swizzle row
 constexpr int kQBlockBytes  = kTileQ * 128;        // one k-block of the query tile: 16 KB
 constexpr int kMaxKBlocks   = 8;                   // dpad <= 512 keeps the query tile resident
 constexpr int kSmemBudget   = 227 * 1024;
@@ -148,7 +156,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for every outstanding tcgen05.ld; the registers are in/out operands so that no use of
+// them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -168,13 +185,55 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
            (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1),
-// A = B = BF16 (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+// A = B = F16 (bits 7-9, 10-12 = 0), both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(m >> 4) << 24);
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------- the kernel ----
+// Candidate lists of this kernel hold RAW pairs {score bits (lo), row (hi)} so that an append is
+// one predicated 8-byte store; compaction converts to ordered keys and back.
+__device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) {
+    return make_key(__uint_as_float(static_cast<uint32_t>(raw)), static_cast<uint32_t>(raw >> 32));
+}
+__device__ __forceinline__ uint64_t key_to_raw(uint64_t key) {
+    return static_cast<uint64_t>(__float_as_uint(key_score(key))) | (static_cast<uint64_t>(key_row(key)) << 32);
+}
+
+// Warp-cooperative compaction of a RAW list to its k best (sorted descending, still raw);
+// returns the k-th best score (or -inf when the list holds fewer than k entries).
+template <int E>
+__device__ __forceinline__ float warp_compact_raw(uint64_t* list, int cnt, int k, int cap, int lane) {
+    if constexpr (E > 0) {
+        uint64_t v[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int g = j * 32 + lane;
+            v[j] = (g < cnt) ? raw_to_key(list[g]) : 0ull;
+        }
+        warp_sort_desc<E>(v, lane);
+        __syncwarp();
+        uint64_t kth = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int g = lane * E + j;
+            if (g < k && g < cnt) list[g] = key_to_raw(v[j]);
+            if (g == k - 1) kth = v[j];
+        }
+        kth = __shfl_sync(0xffffffffu, kth, (k - 1) / E);
+        __syncwarp();
+        return (cnt >= k) ? key_score(kth) : __int_as_float(0xff800000);
+    } else {
+        for (int g = lane; g < cnt; g += 32) list[g] = raw_to_key(list[g]);
+        __syncwarp();
+        const float t = warp_compact_topk_mem(list, cnt, k, cap, lane);
+        const int keep = min(cnt, k);
+        for (int g = lane; g < keep; g += 32) list[g] = key_to_raw(list[g]);
+        __syncwarp();
+        return t;
+    }
+}
+
 struct MmaParams {
     int64_t n_rows;          // rows in this shard
     int     nq;              // real queries
@@ -184,12 +243,68 @@ struct MmaParams {
     int     stages;          // row-tile ring depth
     int     tq;              // query tiles
     int64_t nt;              // row tiles
+    int     ntp;             // row tiles per phase
+    int     phases;
     int     groups;          // CTA groups in the grid
     int     nq_pad;          // tq * 128 * CG
-    uint64_t* lists;         // [grid CTAs][128][C] working candidate lists
+    int     segs_max;        // max query tiles one group touches
+    uint64_t* lists;         // [grid CTAs][segs_max][2 sets][128][C] raw candidate lists
+    int2*     state;         // [grid CTAs][segs_max][2 sets][128] {cnt, tau bits}
+    uint32_t* tau_g;         // [nq_pad] order-preserving encoding of the shared per-query threshold
     uint64_t* out_keys;      // [slots][nq_pad][k]
     int*      out_counts;    // [slots][nq_pad]
 };
+
+// The unit enumeration shared by all warp roles.  A group's unit range inside a phase is
+// [ub, ue) of the query-tile-major linearisation u = t * ntp + jl; it is the same in every phase.
+struct GroupRange {
+    int64_t ub, ue;
+    int t_first, nseg;
+    __device__ GroupRange(const MmaParams& p, int group) {
+        const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
+        ub = Up * group / p.groups; ue = Up * (group + 1) / p.groups;
+        t_first = static_cast<int>(ub / p.ntp);
+        nseg = (ue > ub) ? static_cast<int>((ue - 1) / p.ntp) - t_first + 1 : 0;
+    }
+    // row-tile range [j0, j1) of segment s in phase ph (empty when j0 >= j1)
+    __device__ void tiles(const MmaParams& p, int ph, int s, int64_t& j0, int64_t& j1) const {
+        const int64_t tb = static_cast<int64_t>(t_first + s) * p.ntp;
+        const int64_t jl0 = (ub > tb ? ub : tb) - tb;
+        const int64_t jl1 = (ue < tb + p.ntp ? ue : tb + p.ntp) - tb;
+        j0 = static_cast<int64_t>(ph) * p.ntp + jl0;
+        j1 = static_cast<int64_t>(ph) * p.ntp + jl1;
+        if (j1 > p.nt) j1 = p.nt;
+    }
+    __device__ int count_visits(const MmaParams& p) const {
+        int v = 0;
+        for (int ph = 0; ph < p.phases; ++ph)
+            for (int s = 0; s < nseg; ++s) { int64_t j0, j1; tiles(p, ph, s, j0, j1); v += (j0 < j1); }
+        return v;
+    }
+};
+
+// f_visit(s, t, reload, visit_index) at the start of every non-empty (phase, segment) visit,
+// f_unit(s, t, j, n) for every row tile j (n = running unit counter of this group),
+// f_visit_end(s, t, visit_index) at the end of the visit.  The query tile is (re)loaded at the
+// first visit and, when the group touches more than one query tile, at every visit.
+template <typename FV, typename FU, typename FE>
+__device__ __forceinline__ void for_each_unit(const MmaParams& p, const GroupRange& g, FV&& f_visit, FU&& f_unit,
+                                              FE&& f_visit_end) {
+    int64_t n = 0;
+    int visit = 0;
+    for (int ph = 0; ph < p.phases; ++ph) {
+        for (int s = 0; s < g.nseg; ++s) {
+            int64_t j0, j1;
+            g.tiles(p, ph, s, j0, j1);
+            if (j0 >= j1) continue;
+            const int t = g.t_first + s;
+            f_visit(s, t, visit == 0 || g.nseg > 1, visit);
+            for (int64_t j = j0; j < j1; ++j, ++n) f_unit(s, t, j, n);
+            f_visit_end(s, t, visit);
+            ++visit;
+        }
+    }
+}
 
 template <int CG, int E>
 __global__ void __launch_bounds__(kMmaThreads, 1)
@@ -201,6 +316,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int group = blockIdx.x / CG;
+    const GroupRange gr(p, group);
 
     constexpr int kRowsPerCta = kTileN / CG;                    // rows of each tile this CTA loads
     const uint32_t stage_bytes = kRowsPerCta * 128;
@@ -214,10 +330,6 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     auto tfull_bar  = [&](int a) { return bars + 8u * (34 + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (36 + a); };
     const uint32_t tmem_slot = bars + 8u * 40;
-
-    // work units [u0, u1): unit u = (query tile u / nt, row tile u % nt)
-    const int64_t U = static_cast<int64_t>(p.tq) * p.nt;
-    const int64_t u0 = U * group / p.groups, u1 = U * (group + 1) / p.groups;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -235,146 +347,199 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
     if (warp == 0 && lane == 0) {
         // ============================ TMA producer ============================
-        int stage = 0; uint32_t phase = 0; int seg = 0;
-        for (int64_t u = u0; u < u1; ++u) {
-            const int t = static_cast<int>(u / p.nt);
-            const int64_t j = u % p.nt;
-            if (u == u0 || j == 0) {                              // new query tile
-                if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);   // MMA finished with the old tile
+        int stage = 0; uint32_t phase = 0; int nload = 0;
+        for_each_unit(p, gr,
+            [&](int, int t, bool reload, int) {
+                if (!reload) return;
+                if (nload > 0) mbar_wait(q_empty, (nload - 1) & 1);   // MMA finished with the old query tile
                 if (cta_rank == 0) mbar_expect_tx(q_full, q_bytes * CG);
                 for (int kb = 0; kb < p.kblocks; ++kb)
                     tma_load_2d<CG>(smem_q + kb * kQBlockBytes, &tmap_q, q_full, kb * kKBlock,
                                     t * (kTileQ * CG) + static_cast<int>(cta_rank) * kTileQ);
-                ++seg;
-            }
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_bytes * CG);
-                tma_load_2d<CG>(smem_b + stage * stage_bytes, &tmap_x, full_bar(stage), kb * kKBlock,
-                                static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1 && lane == 0 && cta_rank == 0) {
-        // ============================ MMA issuer ==============================
+                ++nload;
+            },
+            [&](int, int, int64_t j, int64_t) {
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_bytes * CG);
+                    tma_load_2d<CG>(smem_b + stage * stage_bytes, &tmap_x, full_bar(stage), kb * kKBlock,
+                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            },
+            [&](int, int, int) {});
+    } else if (warp == 1 && lane == 0) {
+        // ============================ MMA issuer (leader CTA) =================
+        // q_empty ("the MMAs reading the query tile have retired") is committed at the end of a visit
+        // when a reload follows (group touches > 1 query tile) and at the very last visit.  The
+        // producer consumes all completions but the last; this thread (in both CTAs of a pair) waits
+        // for the last one so that no asynchronous arrive can land after the CTA has retired.
         constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
-        int stage = 0; uint32_t phase = 0; int seg = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = u0; u < u1; ++u) {
-            const int64_t j = u % p.nt;
-            if (u == u0 || j == 0) { mbar_wait(q_full, seg & 1); ++seg; }
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1);            // epilogue drained this accumulator
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-                mbar_wait(full_bar(stage), phase);
+        const int total_visits = gr.count_visits(p);
+        int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0;
+        for_each_unit(p, gr,
+            [&](int, int, bool reload, int) {
+                if (!reload) return;
+                if (cta_rank == 0) mbar_wait(q_full, nload & 1);
+                ++nload;
+            },
+            [&](int, int, int64_t, int64_t n) {
+                if (cta_rank != 0) return;
+                const int acc = static_cast<int>(n & 1);
+                const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);            // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t a0 = smem_q + kb * kQBlockBytes;
-                const uint32_t b0 = smem_b + stage * stage_bytes;
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_q + kb * kQBlockBytes;
+                    const uint32_t b0 = smem_b + stage * stage_bytes;
 #pragma unroll
-                for (int k4 = 0; k4 < kKBlock / 16; ++k4)          // UMMA K = 16 bf16 = 32 bytes
-                    umma_f16<CG>(tmem_d, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
-                                 (kb | k4) ? 1u : 0u);
-                umma_commit<CG>(empty_bar(stage));                 // ring slot free when these MMAs retire
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit<CG>(tfull_bar(acc));                       // accumulator ready for the epilogue
-            if (j == p.nt - 1 || u == u1 - 1) umma_commit<CG>(q_empty);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-        if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);            // last async arrive has landed
-    } else if (warp == 1 && lane == 0 && cta_rank != 0) {
-        // non-leader CTA of a pair: its copy of q_empty receives the multicast arrive of every segment;
-        // wait for the last one so the CTA cannot retire under an in-flight arrive
-        if (u1 > u0) {
-            const int nseg = static_cast<int>((u1 - 1) / p.nt - u0 / p.nt) + 1;
-            mbar_wait(q_empty, (nseg - 1) & 1);
-        }
+                    for (int k4 = 0; k4 < kKBlock / 16; ++k4)          // UMMA K = 16 fp16 = 32 bytes
+                        umma_f16<CG>(tmem_d, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
+                                     (kb | k4) ? 1u : 0u);
+                    umma_commit<CG>(empty_bar(stage));                 // ring slot free when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit<CG>(tfull_bar(acc));                       // accumulator ready for its epilogue set
+            },
+            [&](int, int, int visit) {
+                if (gr.nseg > 1 || visit == total_visits - 1) {
+                    if (cta_rank == 0) umma_commit<CG>(q_empty);
+                    ++ncommit;
+                }
+            });
+        if (ncommit > 0) mbar_wait(q_empty, (ncommit - 1) & 1);
     } else if (warp >= 4) {
         // ============================ epilogue: fused top-k ====================
+        const int set = (warp - 4) >> 2;                           // accumulator / list set 0 or 1
         const int quarter = warp & 3;                              // TMEM lanes [32*quarter, +32)
         const int r = quarter * 32 + lane;                         // query row inside this CTA's tile
-        uint64_t* warp_lists = p.lists + (static_cast<int64_t>(blockIdx.x) * kTileQ + quarter * 32) * p.C;
-        uint64_t* my_list = warp_lists + static_cast<int64_t>(lane) * p.C;
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-        int cnt = 0; float tau = NEG_INF; int acc = 0; uint32_t acc_phase = 0;
-        int cur_t = -1; int64_t q_global = 0;
+        auto list_base = [&](int s, int row) {
+            return p.lists + (((static_cast<int64_t>(blockIdx.x) * p.segs_max + s) * 2 + set) * kTileQ + row) * p.C;
+        };
+        auto state_ptr = [&](int s) {
+            return p.state + ((static_cast<int64_t>(blockIdx.x) * p.segs_max + s) * 2 + set) * kTileQ + r;
+        };
+        for (int s = 0; s < p.segs_max; ++s) *state_ptr(s) = make_int2(0, __float_as_int(NEG_INF));
 
-        auto flush_segment = [&](int t) {
-            // compact every query's list to its sorted top-k and publish it in the slot of (group, t)
-            const int64_t U_ = static_cast<int64_t>(p.tq) * p.nt;
-            const int64_t first_unit = static_cast<int64_t>(t) * p.nt;
-            const int gmin = static_cast<int>(((first_unit + 1) * p.groups - 1) / U_);
-            const int slot = group - gmin;
-            for (int l = 0; l < 32; ++l) {
-                const int c_l = __shfl_sync(0xffffffffu, cnt, l);
-                const int64_t q_l = __shfl_sync(0xffffffffu, q_global, l);
-                if (c_l == 0 || q_l >= p.nq) continue;             // warp-uniform
-                uint64_t* lst = warp_lists + static_cast<int64_t>(l) * p.C;
-                __syncwarp();
-                warp_compact<E>(lst, c_l, p.k, p.C, lane);
-                const int keep = min(c_l, p.k);
-                uint64_t* dst = p.out_keys + (static_cast<int64_t>(slot) * p.nq_pad + q_l) * p.k;
-                for (int i = lane; i < keep; i += 32) dst[i] = lst[i];
-                if (lane == 0) p.out_counts[static_cast<int64_t>(slot) * p.nq_pad + q_l] = keep;
+        int cnt = 0; float tau = NEG_INF; int64_t q_global = 0; bool q_ok = false;
+        uint64_t* my_list = nullptr; uint64_t* warp_lists = nullptr;
+
+        auto compact_lane = [&](int l) {                           // all lanes call; list of lane l
+            const int c_l = __shfl_sync(0xffffffffu, cnt, l);
+            __syncwarp();
+            const float t_l = warp_compact_raw<E>(warp_lists + static_cast<int64_t>(l) * p.C, c_l, p.k, p.C, lane);
+            if (lane == l) {
+                cnt = min(cnt, p.k);
+                if (t_l > tau) tau = t_l;
+                if (q_ok && cnt >= p.k) atomicMax(p.tau_g + q_global, f2ord(t_l));   // share with the other CTAs
             }
         };
-
-        for (int64_t u = u0; u < u1; ++u) {
-            const int t = static_cast<int>(u / p.nt);
-            const int64_t j = u % p.nt;
-            if (t != cur_t) {
-                if (cur_t >= 0) flush_segment(cur_t);
-                cur_t = t;
-                q_global = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
-                cnt = 0;
-                tau = (q_global < p.nq) ? NEG_INF : POS_INF;        // padded queries admit nothing
-            }
-            const int64_t row0 = j * kTileN;
-            const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(acc * kTileN);
-#pragma unroll 1
-            for (int c = 0; c < kTileN / 32; ++c) {
-                // make room: a chunk can add up to 32 entries to one list
-                unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 32);
-                while (need) {
-                    const int l = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int c_l = __shfl_sync(0xffffffffu, cnt, l);
-                    __syncwarp();
-                    const float t_l = warp_compact<E>(warp_lists + static_cast<int64_t>(l) * p.C, c_l, p.k, p.C, lane);
-                    if (lane == l) { tau = t_l; cnt = min(cnt, p.k); }
+        auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
+            // three-input max tree, then a warp vote: most chunks have no survivor
+            float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+            for (int i = 2; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            if (!__any_sync(0xffffffffu, m > tau)) return;
+            const uint32_t rowc = static_cast<uint32_t>(row0) + c * 32;
+            if (nvalid == kTileN) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {                      // branch-free: predicated 8-byte store
+                    const float sc = __uint_as_float(v[i]);
+                    uint64_t* dst = my_list + cnt;
+                    asm volatile(
+                        "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
+                        "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
+                        ::"f"(sc), "f"(tau), "l"(dst), "r"(v[i]), "r"(rowc + i) : "memory");
+                    cnt += (sc > tau) ? 1 : 0;
                 }
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_wait_ld();
-                float m = __uint_as_float(v[0]);
-#pragma unroll
-                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-                if (__any_sync(0xffffffffu, m > tau)) {
-                    const int col0 = c * 32;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v[i]);
-                        if (s > tau && col0 + i < nvalid) {
-                            my_list[cnt] = make_key(s, static_cast<uint32_t>(row0 + col0 + i));
-                            ++cnt;
-                        }
+            } else {                                                // last, partial row tile of the shard
+                for (int i = 0; i < 32; ++i) {
+                    const float sc = __uint_as_float(v[i]);
+                    if (sc > tau && c * 32 + i < nvalid) {
+                        my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
+                        ++cnt;
                     }
                 }
             }
-            // all tcgen05.ld of this accumulator have completed (wait::ld above): hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CG == 1) mbar_arrive_local(tempty_bar(acc));
-                else mbar_arrive_cluster(tempty_bar(acc), 0);
+        };
+
+        for_each_unit(p, gr,
+            [&](int s, int t, bool, int) {                          // visit begin: restore this segment's state
+                q_global = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
+                q_ok = q_global < p.nq;
+                const int2 st = *state_ptr(s);
+                cnt = st.x;
+                tau = q_ok ? __int_as_float(st.y) : POS_INF;        // padded queries admit nothing
+                warp_lists = list_base(s, quarter * 32);
+                my_list = warp_lists + static_cast<int64_t>(lane) * p.C;
+            },
+            [&](int, int, int64_t j, int64_t n) {
+                if (static_cast<int>(n & 1) != set) return;
+                const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
+                const int64_t row0 = j * kTileN;
+                const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
+                if (q_ok) {                                         // fold in the threshold shared by all CTAs
+                    const float tg = ord2f(__ldcg(p.tau_g + q_global));
+                    if (tg > tau) tau = tg;
+                }
+                mbar_wait(tfull_bar(set), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                       static_cast<uint32_t>(set * kTileN);
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; c += 2) {
+                    // make room: two chunks can add up to 64 entries to one list
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
+                    while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
+                    tmem_wait_ld(va);
+                    tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                    process_chunk(va, c, row0, nvalid);
+                    tmem_wait_ld(vb);
+                    if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                    process_chunk(vb, c + 1, row0, nvalid);
+                }
+                // every tcgen05.ld of this accumulator has completed: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive_local(tempty_bar(set));
+                    else mbar_arrive_cluster(tempty_bar(set), 0);
+                }
+            },
+            [&](int s, int, int) {                                  // visit end: park the state
+                *state_ptr(s) = make_int2(cnt, __float_as_int(tau));
+            });
+
+        // final: every (segment, set) list -> sorted top-k keys in its output slot
+        {
+            const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
+            for (int s = 0; s < gr.nseg; ++s) {
+                const int t = gr.t_first + s;
+                const int gmin = static_cast<int>(((static_cast<int64_t>(t) * p.ntp + 1) * p.groups - 1) / Up);
+                const int slot = (group - gmin) * 2 + set;
+                const int2 st = *state_ptr(s);
+                const int64_t qg = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
+                uint64_t* wl = list_base(s, quarter * 32);
+                for (int l = 0; l < 32; ++l) {
+                    const int c_l = __shfl_sync(0xffffffffu, st.x, l);
+                    const int64_t q_l = __shfl_sync(0xffffffffu, qg, l);
+                    if (c_l == 0 || q_l >= p.nq) continue;          // warp-uniform
+                    uint64_t* lst = wl + static_cast<int64_t>(l) * p.C;
+                    __syncwarp();
+                    warp_compact_raw<E>(lst, c_l, p.k, p.C, lane);
+                    const int keep = min(c_l, p.k);
+                    uint64_t* dst = p.out_keys + (static_cast<int64_t>(slot) * p.nq_pad + q_l) * p.k;
+                    for (int i = lane; i < keep; i += 32) dst[i] = raw_to_key(lst[i]);
+                    if (lane == 0) p.out_counts[static_cast<int64_t>(slot) * p.nq_pad + q_l] = keep;
+                }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (cur_t >= 0) flush_segment(cur_t);
     }
 
     // ------------------------------------------------------------------ teardown ----
@@ -383,14 +548,28 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
 }
 
-// fp32 [nq, dim] -> bf16 [nq_pad, dpad], zero padded
-__global__ void queries_to_bf16_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ out,
-                                       int64_t nq, int64_t nq_pad, int dim, int dpad) {
-    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (i >= nq_pad * dpad) return;
-    const int64_t r = i / dpad;
-    const int c = static_cast<int>(i % dpad);
-    out[i] = __float2bfloat16_rn((r < nq && c < dim) ? q[r * dim + c] : 0.f);
+// fp32 [nq, dim] -> fp16 [nq_pad, dpad] (zero padded), one warp per query.  Each query is scaled by
+// a power of two so that its largest component lies in [0.5, 1): exact, keeps fp16 in range for
+// any query norm, and is undone on the final scores (scale[q]).
+__global__ void queries_to_f16_kernel(const float* __restrict__ q, __half* __restrict__ out,
+                                      float* __restrict__ scale, uint32_t* __restrict__ tau_g,
+                                      int64_t nq, int64_t nq_pad, int dim, int dpad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    if (r >= nq_pad) return;
+    float mx = 0.f;
+    if (r < nq)
+        for (int c = lane; c < dim; c += 32) mx = fmaxf(mx, fabsf(q[r * dim + c]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);                 // mx = m * 2^e, m in [0.5, 1)
+    const float down = ldexpf(1.0f, -e);
+    for (int c = lane; c < dpad; c += 32)
+        out[r * dpad + c] = __float2half_rn((r < nq && c < dim) ? q[r * dim + c] * down : 0.f);
+    if (lane == 0) {
+        scale[r] = ldexpf(1.0f, e);
+        tau_g[r] = f2ord(__int_as_float(0xff800000));             // shared threshold starts at -inf
+    }
 }
 
 // ------------------------------------------------------------------ host side ----
@@ -411,7 +590,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
+// 2-D fp16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
 static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int cols, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IVR_ECUDA; }
@@ -419,18 +598,19 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int cols,
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r)); return IVR_ECUDA; }
     return IVR_OK;
 }
 
-static int cta_group_mode() {
-    // IVR_MMA_CTA_GROUP=2 selects the cta_group::2 (CTA pair) variant; read per call so tests can flip it
-    const char* e = getenv("IVR_MMA_CTA_GROUP");
-    return (e && atoi(e) == 2) ? 2 : 1;
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
 }
+// IVR_MMA_CTA_GROUP=2 selects the cta_group::2 (CTA pair) variant; read per call so tests can flip it
+static int cta_group_mode() { return env_int("IVR_MMA_CTA_GROUP", 1) == 2 ? 2 : 1; }
 
 bool mma_supported(const ivr_index* idx, int64_t nq, int k) {
     (void)nq;
@@ -467,44 +647,62 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     p.tq = static_cast<int>((nq + mq - 1) / mq);
     p.nt = (idx->ntotal + kTileN - 1) / kTileN;
     p.nq_pad = p.tq * mq;
+    // phases: row-tile ranges whose rows fit in L2, so that every query tile re-reads them from L2
+    const int64_t phase_bytes = static_cast<int64_t>(std::max(1, env_int("IVR_MMA_PHASE_MB", 48))) << 20;
+    const int64_t ntp_max = std::max<int64_t>(1, phase_bytes / (static_cast<int64_t>(kTileN) * idx->dpad * 2));
+    p.phases = static_cast<int>((p.nt + ntp_max - 1) / ntp_max);
+    p.ntp = static_cast<int>((p.nt + p.phases - 1) / p.phases);
     int grid = idx->sm_count / cg * cg;
     p.groups = grid / cg;
-    const int64_t U = static_cast<int64_t>(p.tq) * p.nt;
-    if (U < p.groups) { p.groups = static_cast<int>(U); grid = p.groups * cg; }
+    const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
+    if (Up < p.groups) { p.groups = static_cast<int>(Up); grid = p.groups * cg; }
     // smem: resident query tile + as many ring stages as fit
     const int stage_bytes = (kTileN / cg) * 128;
     const int q_bytes = p.kblocks * kQBlockBytes;
     p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - q_bytes) / stage_bytes);
     if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the row-tile ring", idx->dim); return IVR_EUNSUPPORTED; }
     const size_t smem = 1024 + q_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
-    // partial-result slots: the groups whose unit range touches one query tile
-    auto g_of = [&](int64_t u) { return static_cast<int>(((u + 1) * p.groups - 1) / U); };
-    int slots = 1;
+    // segments per group and partial-result slots per query tile (mirrors GroupRange on the device)
+    auto g_of = [&](int64_t u) { return static_cast<int>(((u + 1) * p.groups - 1) / Up); };
+    int groups_per_tile = 1;
     for (int t = 0; t < p.tq; ++t)
-        slots = std::max(slots, g_of(static_cast<int64_t>(t) * p.nt + p.nt - 1) - g_of(static_cast<int64_t>(t) * p.nt) + 1);
+        groups_per_tile = std::max(groups_per_tile, g_of(static_cast<int64_t>(t) * p.ntp + p.ntp - 1) -
+                                                    g_of(static_cast<int64_t>(t) * p.ntp) + 1);
+    const int slots = 2 * groups_per_tile;
+    p.segs_max = 1;
+    for (int g = 0; g < p.groups; ++g) {
+        const int64_t ub = Up * g / p.groups, ue = Up * (g + 1) / p.groups;
+        if (ue > ub) p.segs_max = std::max(p.segs_max, static_cast<int>((ue - 1) / p.ntp - ub / p.ntp) + 1);
+    }
 
     // workspace carve-up
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_q = carve(static_cast<size_t>(p.nq_pad) * idx->dpad * 2);
-    const size_t o_l = carve(static_cast<size_t>(grid) * kTileQ * C * 8);
-    const size_t o_k = carve(static_cast<size_t>(slots) * p.nq_pad * k * 8);
-    const size_t o_c = carve(static_cast<size_t>(slots) * p.nq_pad * 4);
+    const size_t o_q  = carve(static_cast<size_t>(p.nq_pad) * idx->dpad * 2);
+    const size_t o_sc = carve(static_cast<size_t>(p.nq_pad) * 4);
+    const size_t o_tg = carve(static_cast<size_t>(p.nq_pad) * 4);
+    const size_t o_l  = carve(static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * C * 8);
+    const size_t o_st = carve(static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * sizeof(int2));
+    const size_t o_k  = carve(static_cast<size_t>(slots) * p.nq_pad * k * 8);
+    const size_t o_c  = carve(static_cast<size_t>(slots) * p.nq_pad * 4);
     const size_t tmp_keys = merge_tmp_entries(slots, nq, k);
-    const size_t o_t = carve(tmp_keys * 8);
+    const size_t o_t  = carve(tmp_keys * 8);
     const size_t o_tc = carve((static_cast<size_t>(slots) * nq + 64) * 4);
     IVR_TRY(ensure_ws(idx, off));
     char* ws = static_cast<char*>(idx->ws);
-    __nv_bfloat16* q_bf = reinterpret_cast<__nv_bfloat16*>(ws + o_q);
+    __half* q_h = reinterpret_cast<__half*>(ws + o_q);
+    float* q_scale = reinterpret_cast<float*>(ws + o_sc);
+    p.tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
     p.lists = reinterpret_cast<uint64_t*>(ws + o_l);
+    p.state = reinterpret_cast<int2*>(ws + o_st);
     p.out_keys = reinterpret_cast<uint64_t*>(ws + o_k);
     p.out_counts = reinterpret_cast<int*>(ws + o_c);
 
     if (idx->timing) cudaEventRecord(idx->ev[4], st);
     {
-        const int64_t n = static_cast<int64_t>(p.nq_pad) * idx->dpad;
-        queries_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(q_dev, q_bf, nq, p.nq_pad,
-                                                                                      idx->dim, idx->dpad);
+        const int64_t threads = static_cast<int64_t>(p.nq_pad) * 32;
+        queries_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+            q_dev, q_h, q_scale, p.tau_g, nq, p.nq_pad, idx->dim, idx->dpad);
         IVR_CUDA(cudaGetLastError());
         idx->launches[2]++;
         IVR_CUDA(cudaMemsetAsync(p.out_counts, 0, static_cast<size_t>(slots) * p.nq_pad * 4, st));
@@ -513,7 +711,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
 
     // TMA descriptors (the row descriptor is cached until the matrix moves or grows)
     CUtensorMap tmq;
-    IVR_TRY(make_tmap(&tmq, q_bf, p.nq_pad, idx->dpad, kTileQ));
+    IVR_TRY(make_tmap(&tmq, q_h, p.nq_pad, idx->dpad, kTileQ));
     if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != kTileN / cg) {
         IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, kTileN / cg));
         idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = kTileN / cg;
@@ -534,7 +732,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     in.cnt_list_stride = p.nq_pad; in.cnt_q_stride = 1;
     in.n_lists = slots; in.fixed_count = 0;
     IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_t),
-                              reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1]));
+                              reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1], q_scale));
     if (idx->timing) {
         cudaEventRecord(idx->ev[3], st);
         idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;

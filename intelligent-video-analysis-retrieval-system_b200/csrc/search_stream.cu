@@ -1,7 +1,7 @@
 // search_stream.cu -- K3: bandwidth-bound small-batch exact search.
 //
 // Replaces index.search(x, k) for nq <= 4 per pass (the reference's production
-// call is nq = 1: unified_index.py:503).  The bf16 row matrix is streamed once
+// call is nq = 1: unified_index.py:503).  The fp16 row matrix is streamed once
 // with 128-bit coalesced, L1-bypassing loads; every 8 lanes own one row, so a
 // warp covers 4 rows per step and keeps 2 steps (8 rows) of loads in flight.
 // Scores are reduced with 3 shuffles and go straight into a per-warp candidate
@@ -23,7 +23,7 @@ constexpr int kUnroll        = 2;              // steps in flight
 
 template <int NQ, int DCH, int E>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
-search_stream_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n_rows, int dpad,
+search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
                      const float* __restrict__ q,      // [NQ, dpad] fp32
                      int k, int C, uint64_t* __restrict__ lists, int* __restrict__ counts) {
     extern __shared__ float s_q[];                     // NQ * dpad
@@ -62,7 +62,7 @@ search_stream_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n_rows, int
             // issue every load of both steps before the first use
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const __nv_bfloat16* rp = rows + (row[u] < 0 ? 0 : row[u]) * dpad + sub * 8;
+                const __half* rp = rows + (row[u] < 0 ? 0 : row[u]) * dpad + sub * 8;
 #pragma unroll
                 for (int c = 0; c < ((DCH > 0) ? DCH : 1); ++c)
                     x[u][c] = (row[u] >= 0) ? ldg_nc_v4(rp + c * 64) : make_uint4(0, 0, 0, 0);
@@ -72,8 +72,8 @@ search_stream_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n_rows, int
 #pragma unroll
                 for (int c = 0; c < ((DCH > 0) ? DCH : 1); ++c) {
                     const uint4 v = x[u][c];
-                    const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
-                    const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+                    const float2 p0 = h2f2(v.x), p1 = h2f2(v.y), p2 = h2f2(v.z), p3 = h2f2(v.w);
+                    const float f0 = p0.x, f1 = p0.y, f2 = p1.x, f3 = p1.y, f4 = p2.x, f5 = p2.y, f6 = p3.x, f7 = p3.y;
 #pragma unroll
                     for (int i = 0; i < NQ; ++i) {
                         const float4 qa = *reinterpret_cast<const float4*>(s_q + i * dpad + c * 64 + sub * 8);
@@ -89,10 +89,10 @@ search_stream_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n_rows, int
             for (int c = 0; c < nch; ++c) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    const __nv_bfloat16* rp = rows + (row[u] < 0 ? 0 : row[u]) * dpad + sub * 8;
+                    const __half* rp = rows + (row[u] < 0 ? 0 : row[u]) * dpad + sub * 8;
                     const uint4 v = (row[u] >= 0) ? ldg_nc_v4(rp + c * 64) : make_uint4(0, 0, 0, 0);
-                    const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
-                    const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+                    const float2 p0 = h2f2(v.x), p1 = h2f2(v.y), p2 = h2f2(v.z), p3 = h2f2(v.w);
+                    const float f0 = p0.x, f1 = p0.y, f2 = p1.x, f3 = p1.y, f4 = p2.x, f5 = p2.y, f6 = p3.x, f7 = p3.y;
 #pragma unroll
                     for (int i = 0; i < NQ; ++i) {
                         const float4 qa = *reinterpret_cast<const float4*>(s_q + i * dpad + c * 64 + sub * 8);

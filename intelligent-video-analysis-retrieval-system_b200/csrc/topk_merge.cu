@@ -19,6 +19,7 @@ struct MergeOut {
     float*    D;            // final
     int64_t*  I;
     int64_t   id_offset;
+    const float* q_scale;   // final: per-query score multiplier (nullptr = 1)
     uint64_t* entries;      // non-final: [groups, nq, k]
     int*      counts;       // non-final: [groups, nq]
     int64_t   nq;
@@ -122,10 +123,11 @@ merge_kernel(MergeIn in, MergeOut out, int lists_per_group, int k, int kpad) {
 
     const int nvalid = min(total, k);
     if (FINAL) {
+        const float scale = out.q_scale ? out.q_scale[q] : 1.0f;
         for (int i = tid; i < k; i += blockDim.x) {
             const uint64_t key = s_keys[i];
             const bool ok = i < nvalid;
-            out.D[q * k + i] = ok ? key_score(key) : -3.402823466e+38f;
+            out.D[q * k + i] = ok ? key_score(key) * scale : -3.402823466e+38f;
             out.I[q * k + i] = ok ? static_cast<int64_t>(key_row(key)) + out.id_offset : -1;
         }
     } else {
@@ -147,7 +149,7 @@ size_t merge_tmp_entries(int n_lists, int64_t nq, int k) {
 
 int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                       int64_t id_offset, uint64_t* tmp_entries, int* tmp_counts,
-                      cudaStream_t st, int* n_launches) {
+                      cudaStream_t st, int* n_launches, const float* q_scale) {
     if (nq <= 0) return IVR_OK;
     const int kpad = kpad_for(k);
     const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
@@ -175,7 +177,7 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
         if (++level > 4) { set_error("merge: too many levels"); return IVR_EINVAL; }
     }
     MergeOut out{};
-    out.D = D_dev; out.I = I_dev; out.id_offset = id_offset; out.nq = nq;
+    out.D = D_dev; out.I = I_dev; out.id_offset = id_offset; out.nq = nq; out.q_scale = q_scale;
     dim3 grid(static_cast<unsigned>(nq), 1);
     merge_kernel<true><<<grid, kMergeThreads, smem, st>>>(in, out, in.n_lists, k, kpad);
     IVR_CUDA(cudaGetLastError());
