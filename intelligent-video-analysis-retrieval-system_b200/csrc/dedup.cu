@@ -16,6 +16,8 @@
 // on the bit masks alone (O(1) per frame with a W-bit keep history).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace ivr {
 
 constexpr int kDedupWarps = 8;                 // frames per batch and per CTA
@@ -67,9 +69,10 @@ banded_cosine_kernel(const float* __restrict__ e, int64_t n, int d, int window, 
                 for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 float nrm = sqrtf(ss);
                 if (nrm == 0.f) nrm = 1.f;                                   // sklearn: 0 -> 1
+                const float inv = 1.0f / nrm;
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
-                    cur[j].x /= nrm; cur[j].y /= nrm; cur[j].z /= nrm; cur[j].w /= nrm;
+                    cur[j].x *= inv; cur[j].y *= inv; cur[j].z *= inv; cur[j].w *= inv;
                     reinterpret_cast<float4*>(slot)[lane + 32 * j] = cur[j];
                 }
             } else {
@@ -112,6 +115,131 @@ banded_cosine_kernel(const float* __restrict__ e, int64_t n, int d, int window, 
         }
         // ring holds window + 2 batches: the next batch's writes cannot touch rows this
         // batch still reads, so one barrier per batch is enough.
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Register-tiled variant for window <= 8 and d in {384, 512}: a warp owns FOUR consecutive frames,
+// so a parked row read from shared memory is reused by up to four dot products (11 row reads per
+// 32 dots instead of 32), and the 32 partial sums of a group are reduced with one 31-shuffle
+// transpose-reduction that leaves dot (frame g, offset dd) in lane 8*g + dd - 1.
+// ---------------------------------------------------------------------------
+constexpr int kG = 4;                           // frames per warp per batch
+constexpr int kG4Warps = 4;
+constexpr int kG4Batch = kG * kG4Warps;         // 16 frames per batch
+constexpr int kG4Window = 8;                    // offsets computed per frame
+constexpr int kG4Ring = kG4Window + 2 * kG4Batch;
+
+template <int DV>
+__global__ void __launch_bounds__(kG4Warps * 32, 2)
+banded_cosine_g4_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
+                        uint32_t* __restrict__ masks, float* __restrict__ cos_prev) {
+    extern __shared__ float s_ring[];          // kG4Ring rows of DV*128 floats
+    constexpr int RS = DV * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t f0 = n * blockIdx.x / gridDim.x, f1 = n * (blockIdx.x + 1) / gridDim.x;
+    if (f0 >= f1) return;
+    const int64_t fs = (f0 - kG4Window > 0) ? f0 - kG4Window : 0;
+
+    float4 cur[kG][DV], nxt[kG][DV];
+    auto load_group = [&](int64_t i0, float4 (&r)[kG][DV]) {
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+            const int64_t i = i0 + g;
+            const float4* p = reinterpret_cast<const float4*>(e + (i < f1 ? i : f1 - 1) * RS);
+#pragma unroll
+            for (int j = 0; j < DV; ++j) r[g][j] = ldg_nc_f4(p + lane + 32 * j);
+        }
+    };
+    int64_t base = fs;
+    load_group(base + warp * kG, nxt);
+
+    for (; base < f1; base += kG4Batch) {
+        const int64_t i0 = base + warp * kG;
+#pragma unroll
+        for (int g = 0; g < kG; ++g)
+#pragma unroll
+            for (int j = 0; j < DV; ++j) cur[g][j] = nxt[g][j];
+        if (base + kG4Batch < f1) load_group(i0 + kG4Batch, nxt);          // prefetch the next batch
+
+        // normalise the four rows (sklearn order: x / ||x||, zero norm -> 1) and park them
+        float ss[kG];
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < DV; ++j) {
+                a = fmaf(cur[g][j].x, cur[g][j].x, a); a = fmaf(cur[g][j].y, cur[g][j].y, a);
+                a = fmaf(cur[g][j].z, cur[g][j].z, a); a = fmaf(cur[g][j].w, cur[g][j].w, a);
+            }
+            ss[g] = a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int g = 0; g < kG; ++g) ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
+#pragma unroll
+        for (int g = 0; g < kG; ++g) {
+            float nrm = sqrtf(ss[g]);
+            if (nrm == 0.f) nrm = 1.f;
+            const float inv = 1.0f / nrm;
+            float4* slot = reinterpret_cast<float4*>(s_ring + static_cast<size_t>((i0 + g) % kG4Ring) * RS);
+#pragma unroll
+            for (int j = 0; j < DV; ++j) {
+                cur[g][j].x *= inv; cur[g][j].y *= inv; cur[g][j].z *= inv; cur[g][j].w *= inv;
+                if (i0 + g < f1) slot[lane + 32 * j] = cur[g][j];
+            }
+        }
+        __syncthreads();
+
+        if (i0 < f1 && i0 + kG > f0) {                                      // warp-uniform: some live frame
+            float acc[kG * kG4Window];
+#pragma unroll
+            for (int a = 0; a < kG * kG4Window; ++a) acc[a] = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < kG4Window + kG - 1; ++rr) {
+                const int64_t r = i0 - kG4Window + rr;
+                if (r < 0) continue;                                        // warp-uniform
+                const float4* other = reinterpret_cast<const float4*>(s_ring + static_cast<size_t>(r % kG4Ring) * RS);
+                float4 o[DV];
+#pragma unroll
+                for (int j = 0; j < DV; ++j) o[j] = other[lane + 32 * j];
+#pragma unroll
+                for (int g = 0; g < kG; ++g) {
+                    const int dd = kG4Window + g - rr;                      // frame i0+g minus row r
+                    if (dd >= 1 && dd <= kG4Window) {
+                        float a = acc[g * kG4Window + dd - 1];
+#pragma unroll
+                        for (int j = 0; j < DV; ++j) {
+                            a = fmaf(cur[g][j].x, o[j].x, a); a = fmaf(cur[g][j].y, o[j].y, a);
+                            a = fmaf(cur[g][j].z, o[j].z, a); a = fmaf(cur[g][j].w, o[j].w, a);
+                        }
+                        acc[g * kG4Window + dd - 1] = a;
+                    }
+                }
+            }
+            // transpose-reduce: after the 5 steps lane l holds the full sum of acc index l
+#pragma unroll
+            for (int s = 16, half = 16; s > 0; s >>= 1, half >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int a = 0; a < half; ++a) {
+                    const float send = up ? acc[a] : acc[a + half];
+                    const float keep = up ? acc[a + half] : acc[a];
+                    acc[a] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            const float val = acc[0];
+            const int g = lane >> 3, dd = (lane & 7) + 1;
+            const int64_t i = i0 + g, j = i - dd;
+            const bool live = i >= f0 && i < f1;
+            const bool ge = live && dd <= window && j >= 0 && val >= thr;
+            const unsigned ballot = __ballot_sync(0xffffffffu, ge);
+            if (live && dd == 1) {
+                if (masks) masks[i] = (ballot >> (8 * g)) & 0xffu;
+                if (cos_prev) cos_prev[i] = (j >= 0) ? val : 1.0f;
+            }
+        }
     }
 }
 
@@ -191,12 +319,37 @@ int dedup_last_timing(float ms[2]) {
     return IVR_OK;
 }
 
+static int env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, uint32_t* masks,
                   float* cos_prev, int sm_count, cudaStream_t st) {
     if (n <= 0) return IVR_OK;
+    const bool aligned = (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0;
+    // register-tiled kernel: window <= 8, d = 384 or 512 (IVR_DEDUP_SIMPLE=1 forces the generic one)
+    if (aligned && window <= kG4Window && (d == 512 || d == 384) && !env_flag("IVR_DEDUP_SIMPLE", 0)) {
+        const size_t smem = static_cast<size_t>(kG4Ring) * d * sizeof(float);
+        int64_t grid = static_cast<int64_t>(sm_count) * 4;
+        const int64_t max_grid = (n + 127) / 128;
+        if (grid > max_grid) grid = max_grid;
+        if (grid < 1) grid = 1;
+        if (d == 512) {
+            auto kern = banded_cosine_g4_kernel<4>;
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<static_cast<unsigned>(grid), kG4Warps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+        } else {
+            auto kern = banded_cosine_g4_kernel<3>;
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<static_cast<unsigned>(grid), kG4Warps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+        }
+        IVR_CUDA(cudaGetLastError());
+        return IVR_OK;
+    }
     const int ring = window + 2 * kDedupWarps;
     int dv = 0;
-    if (d % 128 == 0 && (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0) dv = d / 128;
+    if (d % 128 == 0 && aligned) dv = d / 128;
     const int dstride = dv ? d : (d + 3) / 4 * 4;
     const size_t smem = static_cast<size_t>(ring) * dstride * sizeof(float);
     if (smem > 227 * 1024) {

@@ -60,12 +60,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `cta` of the cluster
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  Relaxed: the only thing
+// the waiter (the MMA issuer) consumes is TMEM, ordered by tcgen05.wait::ld + tcgen05.fence.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -87,18 +88,26 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                            uint64_t policy) {
     if constexpr (CG == 1) {
         asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "l"(policy) : "memory");
     } else {
         // both CTAs of the pair signal the LEADER's barrier (peer bit cleared)
         asm volatile(
-            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y) : "memory");
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y), "l"(policy)
+            : "memory");
     }
 }
+// L2 eviction-priority descriptors (same encodings as cute::TMA::CacheHintSm90)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst  = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast   = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -248,6 +257,7 @@ struct MmaParams {
     int     groups;          // CTA groups in the grid
     int     nq_pad;          // tq * 128 * CG
     int     segs_max;        // max query tiles one group touches
+    uint64_t row_policy;     // L2 eviction priority of the row-tile loads
     uint64_t* lists;         // [grid CTAs][segs_max][2 sets][128][C] raw candidate lists
     int2*     state;         // [grid CTAs][segs_max][2 sets][128] {cnt, tau bits}
     uint32_t* tau_g;         // [nq_pad] order-preserving encoding of the shared per-query threshold
@@ -275,34 +285,50 @@ struct GroupRange {
         j1 = static_cast<int64_t>(ph) * p.ntp + jl1;
         if (j1 > p.nt) j1 = p.nt;
     }
-    __device__ int count_visits(const MmaParams& p) const {
-        int v = 0;
-        for (int ph = 0; ph < p.phases; ++ph)
-            for (int s = 0; s < nseg; ++s) { int64_t j0, j1; tiles(p, ph, s, j0, j1); v += (j0 < j1); }
-        return v;
-    }
 };
 
 // f_visit(s, t, reload, visit_index) at the start of every non-empty (phase, segment) visit,
 // f_unit(s, t, j, n) for every row tile j (n = running unit counter of this group),
-// f_visit_end(s, t, visit_index) at the end of the visit.  The query tile is (re)loaded at the
-// first visit and, when the group touches more than one query tile, at every visit.
+// f_visit_end(s, t, visit_index, next_reload) at the end of the visit.  Odd phases walk the
+// segments backwards, so a group that touches two query tiles reloads the resident query tile
+// once per phase instead of twice; `reload` is set exactly when the query tile changes.
 template <typename FV, typename FU, typename FE>
 __device__ __forceinline__ void for_each_unit(const MmaParams& p, const GroupRange& g, FV&& f_visit, FU&& f_unit,
                                               FE&& f_visit_end) {
     int64_t n = 0;
     int visit = 0;
-    for (int ph = 0; ph < p.phases; ++ph) {
-        for (int s = 0; s < g.nseg; ++s) {
+    int loaded_t = -1;
+    // current visit
+    int ph = 0, si = 0;
+    auto seg_of = [&](int ph_, int si_) { return (ph_ & 1) ? g.nseg - 1 - si_ : si_; };
+    auto advance = [&](int& ph_, int& si_) { if (++si_ == g.nseg) { si_ = 0; ++ph_; } };
+    auto skip_empty = [&](int& ph_, int& si_) {
+        while (ph_ < p.phases) {
             int64_t j0, j1;
-            g.tiles(p, ph, s, j0, j1);
-            if (j0 >= j1) continue;
-            const int t = g.t_first + s;
-            f_visit(s, t, visit == 0 || g.nseg > 1, visit);
-            for (int64_t j = j0; j < j1; ++j, ++n) f_unit(s, t, j, n);
-            f_visit_end(s, t, visit);
-            ++visit;
+            g.tiles(p, ph_, seg_of(ph_, si_), j0, j1);
+            if (j0 < j1) return true;
+            advance(ph_, si_);
         }
+        return false;
+    };
+    if (g.nseg == 0 || !skip_empty(ph, si)) return;
+    while (true) {
+        const int s = seg_of(ph, si);
+        const int t = g.t_first + s;
+        int64_t j0, j1;
+        g.tiles(p, ph, s, j0, j1);
+        // look ahead: does the next visit need another query tile?
+        int nph = ph, nsi = si;
+        advance(nph, nsi);
+        const bool has_next = skip_empty(nph, nsi);
+        const bool next_reload = has_next && (g.t_first + seg_of(nph, nsi) != t);
+        f_visit(s, t, t != loaded_t, visit);
+        loaded_t = t;
+        for (int64_t j = j0; j < j1; ++j, ++n) f_unit(s, t, j, n);
+        f_visit_end(s, t, visit, next_reload || !has_next);
+        ++visit;
+        if (!has_next) break;
+        ph = nph; si = nsi;
     }
 }
 
@@ -347,35 +373,46 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
     if (warp == 0 && lane == 0) {
         // ============================ TMA producer ============================
+        // At a query-tile switch the first ring-full of row tiles of the new visit is issued BEFORE
+        // waiting for the MMAs of the old visit to release the resident query tile, so the ring is
+        // already full when the new query tile lands.
         int stage = 0; uint32_t phase = 0; int nload = 0;
+        bool pending_q = false; int pending_t = 0; int issued_since = 0;
+        auto load_q = [&]() {
+            if (nload > 0) mbar_wait(q_empty, (nload - 1) & 1);       // MMAs finished with the old query tile
+            if (cta_rank == 0) mbar_expect_tx(q_full, q_bytes * CG);
+            for (int kb = 0; kb < p.kblocks; ++kb)
+                tma_load_2d<CG>(smem_q + kb * kQBlockBytes, &tmap_q, q_full, kb * kKBlock,
+                                pending_t * (kTileQ * CG) + static_cast<int>(cta_rank) * kTileQ, kL2EvictLast);
+            ++nload;
+            pending_q = false;
+        };
         for_each_unit(p, gr,
             [&](int, int t, bool reload, int) {
                 if (!reload) return;
-                if (nload > 0) mbar_wait(q_empty, (nload - 1) & 1);   // MMA finished with the old query tile
-                if (cta_rank == 0) mbar_expect_tx(q_full, q_bytes * CG);
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d<CG>(smem_q + kb * kQBlockBytes, &tmap_q, q_full, kb * kKBlock,
-                                    t * (kTileQ * CG) + static_cast<int>(cta_rank) * kTileQ);
-                ++nload;
+                pending_q = true; pending_t = t; issued_since = 0;
+                if (nload == 0) load_q();                              // very first tile: nothing to overlap
             },
             [&](int, int, int64_t j, int64_t) {
                 for (int kb = 0; kb < p.kblocks; ++kb) {
+                    if (pending_q && issued_since >= p.stages) load_q();
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_bytes * CG);
                     tma_load_2d<CG>(smem_b + stage * stage_bytes, &tmap_x, full_bar(stage), kb * kKBlock,
-                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta);
+                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta,
+                                    p.row_policy);
+                    ++issued_since;
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             },
-            [&](int, int, int) {});
+            [&](int, int, int, bool) { if (pending_q) load_q(); });
     } else if (warp == 1 && lane == 0) {
         // ============================ MMA issuer (leader CTA) =================
         // q_empty ("the MMAs reading the query tile have retired") is committed at the end of a visit
-        // when a reload follows (group touches > 1 query tile) and at the very last visit.  The
+        // when the next visit needs another query tile and at the very last visit.  The
         // producer consumes all completions but the last; this thread (in both CTAs of a pair) waits
         // for the last one so that no asynchronous arrive can land after the CTA has retired.
         constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
-        const int total_visits = gr.count_visits(p);
         int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0;
         for_each_unit(p, gr,
             [&](int, int, bool reload, int) {
@@ -404,8 +441,8 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
                 umma_commit<CG>(tfull_bar(acc));                       // accumulator ready for its epilogue set
             },
-            [&](int, int, int visit) {
-                if (gr.nseg > 1 || visit == total_visits - 1) {
+            [&](int, int, int, bool release_q) {
+                if (release_q) {
                     if (cta_rank == 0) umma_commit<CG>(q_empty);
                     ++ncommit;
                 }
@@ -474,6 +511,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const int2 st = *state_ptr(s);
                 cnt = st.x;
                 tau = q_ok ? __int_as_float(st.y) : POS_INF;        // padded queries admit nothing
+                if (q_ok) tau = fmaxf(tau, ord2f(__ldcg(p.tau_g + q_global)));
                 warp_lists = list_base(s, quarter * 32);
                 my_list = warp_lists + static_cast<int64_t>(lane) * p.C;
             },
@@ -482,10 +520,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
                 const int64_t row0 = j * kTileN;
                 const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
-                if (q_ok) {                                         // fold in the threshold shared by all CTAs
-                    const float tg = ord2f(__ldcg(p.tau_g + q_global));
-                    if (tg > tau) tau = tg;
-                }
+                // the threshold shared by all CTAs: issue the load now, fold it in after this tile
+                // (its L2 latency hides behind the chunk loop)
+                const uint32_t tg_bits = q_ok ? __ldcg(p.tau_g + q_global) : 0u;
                 mbar_wait(tfull_bar(set), acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -504,6 +541,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
                     process_chunk(vb, c + 1, row0, nvalid);
                 }
+                if (q_ok) tau = fmaxf(tau, ord2f(tg_bits));
                 // every tcgen05.ld of this accumulator has completed: hand it back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
@@ -512,7 +550,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     else mbar_arrive_cluster(tempty_bar(set), 0);
                 }
             },
-            [&](int s, int, int) {                                  // visit end: park the state
+            [&](int s, int, int, bool) {                            // visit end: park the state
                 *state_ptr(s) = make_int2(cnt, __float_as_int(tau));
             });
 
@@ -669,6 +707,10 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
         groups_per_tile = std::max(groups_per_tile, g_of(static_cast<int64_t>(t) * p.ntp + p.ntp - 1) -
                                                     g_of(static_cast<int64_t>(t) * p.ntp) + 1);
     const int slots = 2 * groups_per_tile;
+    {
+        const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
+        p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
+    }
     p.segs_max = 1;
     for (int g = 0; g < p.groups; ++g) {
         const int64_t ub = Up * g / p.groups, ue = Up * (g + 1) / p.groups;
