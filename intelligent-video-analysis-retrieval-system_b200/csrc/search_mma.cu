@@ -8,12 +8,13 @@
 //
 // One persistent CTA per SM (CG = 1) or one CTA pair per TPC (CG = 2,
 // tcgen05 cta_group::2).  A work unit is a (128*CG queries) x (256 rows) tile.
-//   * SCHEDULE.  The row tiles are cut into PHASES whose rows fit in L2 (default 48 MB).
-//     Inside a phase the (query tile, row tile) units are linearised query-tile-major and
-//     split into equal contiguous ranges, one per CTA group, the same split in every phase:
-//     a group works on the same <= 2-3 query tiles for the whole kernel, every group has
-//     the same MMA work, and each row is fetched from HBM once per search (the other
-//     query tiles hit it in L2).
+//   * SCHEDULE.  With G CTA groups and Tq query tiles, c = floor(G / Tq) groups are bound to every
+//     query tile for the whole kernel (the "grid" part, c * Tq groups): group (t, i) owns query
+//     tile t and walks the row tiles i, i + c, i + 2c, ... -- so at any moment all Tq query tiles
+//     are working on the same c row tiles: the first group to touch a row tile fetches it from
+//     HBM, the other Tq - 1 hit it in L2 (measured: without this lockstep every query tile
+//     re-read the rows from HBM).  The G - c * Tq leftover groups take the last
+//     (G - c*Tq)/G of the row tiles, query-tile-major, so every group has the same MMA work.
 //   * the query tile stays RESIDENT in shared memory (dpad <= 512: 128 x dpad fp16
 //     = 128 KB) -- only the row tiles stream through a TMA/mbarrier ring, which
 //     halves the L2->SMEM traffic of a classic GEMM tile loop;
@@ -252,9 +253,10 @@ struct MmaParams {
     int     stages;          // row-tile ring depth
     int     tq;              // query tiles
     int64_t nt;              // row tiles
-    int     ntp;             // row tiles per phase
-    int     phases;
-    int     groups;          // CTA groups in the grid
+    int     c;               // grid groups per query tile
+    int     g_grid;          // c * tq groups walk rows [0, ntg) in lockstep
+    int64_t ntg;             // row tiles of the grid part; the leftover groups own [ntg, nt)
+    int     groups;          // CTA groups in the launch
     int     nq_pad;          // tq * 128 * CG
     int     segs_max;        // max query tiles one group touches
     uint64_t row_policy;     // L2 eviction priority of the row-tile loads
@@ -265,70 +267,47 @@ struct MmaParams {
     int*      out_counts;    // [slots][nq_pad]
 };
 
-// The unit enumeration shared by all warp roles.  A group's unit range inside a phase is
-// [ub, ue) of the query-tile-major linearisation u = t * ntp + jl; it is the same in every phase.
-struct GroupRange {
-    int64_t ub, ue;
+// The unit enumeration shared by all warp roles.
+//   f_visit(s, t, reload, visit)            start of the visit of segment s (query tile t)
+//   f_unit(s, t, j, n)                      row tile j; n = running unit counter of this group
+//   f_visit_end(s, t, visit, release_q)     end of the visit
+// A grid group has one segment (its query tile) and a strided walk over [0, ntg); a leftover group
+// walks a contiguous range of the query-tile-major units over the row tiles [ntg, nt).
+struct LeftRange {                      // leftover group: units u = t * ntl + jl
+    int64_t ub, ue, ntl;
     int t_first, nseg;
-    __device__ GroupRange(const MmaParams& p, int group) {
-        const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
-        ub = Up * group / p.groups; ue = Up * (group + 1) / p.groups;
-        t_first = static_cast<int>(ub / p.ntp);
-        nseg = (ue > ub) ? static_cast<int>((ue - 1) / p.ntp) - t_first + 1 : 0;
-    }
-    // row-tile range [j0, j1) of segment s in phase ph (empty when j0 >= j1)
-    __device__ void tiles(const MmaParams& p, int ph, int s, int64_t& j0, int64_t& j1) const {
-        const int64_t tb = static_cast<int64_t>(t_first + s) * p.ntp;
-        const int64_t jl0 = (ub > tb ? ub : tb) - tb;
-        const int64_t jl1 = (ue < tb + p.ntp ? ue : tb + p.ntp) - tb;
-        j0 = static_cast<int64_t>(ph) * p.ntp + jl0;
-        j1 = static_cast<int64_t>(ph) * p.ntp + jl1;
-        if (j1 > p.nt) j1 = p.nt;
+    __device__ LeftRange(const MmaParams& p, int group) {
+        const int gl = group - p.g_grid, Gl = p.groups - p.g_grid;
+        ntl = p.nt - p.ntg;
+        const int64_t Ul = static_cast<int64_t>(p.tq) * ntl;
+        ub = Ul * gl / Gl; ue = Ul * (gl + 1) / Gl;
+        t_first = (ntl > 0) ? static_cast<int>(ub / ntl) : 0;
+        nseg = (ue > ub) ? static_cast<int>((ue - 1) / ntl) - t_first + 1 : 0;
     }
 };
 
-// f_visit(s, t, reload, visit_index) at the start of every non-empty (phase, segment) visit,
-// f_unit(s, t, j, n) for every row tile j (n = running unit counter of this group),
-// f_visit_end(s, t, visit_index, next_reload) at the end of the visit.  Odd phases walk the
-// segments backwards, so a group that touches two query tiles reloads the resident query tile
-// once per phase instead of twice; `reload` is set exactly when the query tile changes.
 template <typename FV, typename FU, typename FE>
-__device__ __forceinline__ void for_each_unit(const MmaParams& p, const GroupRange& g, FV&& f_visit, FU&& f_unit,
+__device__ __forceinline__ void for_each_unit(const MmaParams& p, int group, FV&& f_visit, FU&& f_unit,
                                               FE&& f_visit_end) {
-    int64_t n = 0;
-    int visit = 0;
-    int loaded_t = -1;
-    // current visit
-    int ph = 0, si = 0;
-    auto seg_of = [&](int ph_, int si_) { return (ph_ & 1) ? g.nseg - 1 - si_ : si_; };
-    auto advance = [&](int& ph_, int& si_) { if (++si_ == g.nseg) { si_ = 0; ++ph_; } };
-    auto skip_empty = [&](int& ph_, int& si_) {
-        while (ph_ < p.phases) {
-            int64_t j0, j1;
-            g.tiles(p, ph_, seg_of(ph_, si_), j0, j1);
-            if (j0 < j1) return true;
-            advance(ph_, si_);
+    if (group < p.g_grid) {
+        const int t = group % p.tq, i = group / p.tq;
+        if (i >= p.ntg) return;
+        f_visit(0, t, true, 0);
+        int64_t n = 0;
+        for (int64_t j = i; j < p.ntg; j += p.c, ++n) f_unit(0, t, j, n);
+        f_visit_end(0, t, 0, true);
+    } else {
+        const LeftRange lr(p, group);
+        int64_t n = 0;
+        for (int s = 0; s < lr.nseg; ++s) {
+            const int t = lr.t_first + s;
+            const int64_t tb = static_cast<int64_t>(t) * lr.ntl;
+            const int64_t j0 = p.ntg + (lr.ub > tb ? lr.ub : tb) - tb;
+            const int64_t j1 = p.ntg + (lr.ue < tb + lr.ntl ? lr.ue : tb + lr.ntl) - tb;
+            f_visit(s, t, true, s);
+            for (int64_t j = j0; j < j1; ++j, ++n) f_unit(s, t, j, n);
+            f_visit_end(s, t, s, true);
         }
-        return false;
-    };
-    if (g.nseg == 0 || !skip_empty(ph, si)) return;
-    while (true) {
-        const int s = seg_of(ph, si);
-        const int t = g.t_first + s;
-        int64_t j0, j1;
-        g.tiles(p, ph, s, j0, j1);
-        // look ahead: does the next visit need another query tile?
-        int nph = ph, nsi = si;
-        advance(nph, nsi);
-        const bool has_next = skip_empty(nph, nsi);
-        const bool next_reload = has_next && (g.t_first + seg_of(nph, nsi) != t);
-        f_visit(s, t, t != loaded_t, visit);
-        loaded_t = t;
-        for (int64_t j = j0; j < j1; ++j, ++n) f_unit(s, t, j, n);
-        f_visit_end(s, t, visit, next_reload || !has_next);
-        ++visit;
-        if (!has_next) break;
-        ph = nph; si = nsi;
     }
 }
 
@@ -342,7 +321,6 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int group = blockIdx.x / CG;
-    const GroupRange gr(p, group);
 
     constexpr int kRowsPerCta = kTileN / CG;                    // rows of each tile this CTA loads
     const uint32_t stage_bytes = kRowsPerCta * 128;
@@ -387,7 +365,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             ++nload;
             pending_q = false;
         };
-        for_each_unit(p, gr,
+        for_each_unit(p, group,
             [&](int, int t, bool reload, int) {
                 if (!reload) return;
                 pending_q = true; pending_t = t; issued_since = 0;
@@ -414,7 +392,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // for the last one so that no asynchronous arrive can land after the CTA has retired.
         constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
         int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0;
-        for_each_unit(p, gr,
+        for_each_unit(p, group,
             [&](int, int, bool reload, int) {
                 if (!reload) return;
                 if (cta_rank == 0) mbar_wait(q_full, nload & 1);
@@ -504,7 +482,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         };
 
-        for_each_unit(p, gr,
+        for_each_unit(p, group,
             [&](int s, int t, bool, int) {                          // visit begin: restore this segment's state
                 q_global = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
                 q_ok = q_global < p.nq;
@@ -554,13 +532,26 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 *state_ptr(s) = make_int2(cnt, __float_as_int(tau));
             });
 
-        // final: every (segment, set) list -> sorted top-k keys in its output slot
+        // final: every (segment, set) list -> sorted top-k keys in its output slot.  Slots of a query
+        // tile: the c grid groups first, then the leftover groups that touch it.
         {
-            const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
-            for (int s = 0; s < gr.nseg; ++s) {
-                const int t = gr.t_first + s;
-                const int gmin = static_cast<int>(((static_cast<int64_t>(t) * p.ntp + 1) * p.groups - 1) / Up);
-                const int slot = (group - gmin) * 2 + set;
+            int t_first, nseg, slot0_first;
+            if (group < p.g_grid) {
+                t_first = group % p.tq; nseg = (group / p.tq < p.ntg) ? 1 : 0; slot0_first = group / p.tq;
+            } else {
+                const LeftRange lr(p, group);
+                t_first = lr.t_first; nseg = lr.nseg; slot0_first = -1;
+            }
+            for (int s = 0; s < nseg; ++s) {
+                const int t = t_first + s;
+                int slot_g = slot0_first;
+                if (slot_g < 0) {                                   // leftover: index among the leftover groups of t
+                    const int Gl = p.groups - p.g_grid;
+                    const int64_t ntl = p.nt - p.ntg, Ul = static_cast<int64_t>(p.tq) * ntl;
+                    const int glmin = static_cast<int>(((static_cast<int64_t>(t) * ntl + 1) * Gl - 1) / Ul);
+                    slot_g = p.c + (group - p.g_grid - glmin);
+                }
+                const int slot = slot_g * 2 + set;
                 const int2 st = *state_ptr(s);
                 const int64_t qg = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
                 uint64_t* wl = list_base(s, quarter * 32);
@@ -673,9 +664,8 @@ static int launch_mma(const CUtensorMap& tq, const CUtensorMap& tx, const MmaPar
     return IVR_OK;
 }
 
-int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
-               int64_t id_offset, cudaStream_t st) {
-    const int cg = cta_group_mode();
+static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                            int64_t id_offset, cudaStream_t st, int cg, bool first_batch) {
     const int kcap = kcap_for(k);
     const int C = 2 * kcap;
     const int mq = kTileQ * cg;
@@ -685,37 +675,39 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     p.tq = static_cast<int>((nq + mq - 1) / mq);
     p.nt = (idx->ntotal + kTileN - 1) / kTileN;
     p.nq_pad = p.tq * mq;
-    // phases: row-tile ranges whose rows fit in L2, so that every query tile re-reads them from L2
-    const int64_t phase_bytes = static_cast<int64_t>(std::max(1, env_int("IVR_MMA_PHASE_MB", 48))) << 20;
-    const int64_t ntp_max = std::max<int64_t>(1, phase_bytes / (static_cast<int64_t>(kTileN) * idx->dpad * 2));
-    p.phases = static_cast<int>((p.nt + ntp_max - 1) / ntp_max);
-    p.ntp = static_cast<int>((p.nt + p.phases - 1) / p.phases);
     int grid = idx->sm_count / cg * cg;
-    p.groups = grid / cg;
-    const int64_t Up = static_cast<int64_t>(p.tq) * p.ntp;
-    if (Up < p.groups) { p.groups = static_cast<int>(Up); grid = p.groups * cg; }
+    p.groups = grid / cg;                                          // caller guarantees tq <= groups
+    // lockstep grid part + leftover part with equal work per group
+    p.c = p.groups / p.tq;
+    p.g_grid = p.c * p.tq;
+    p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
+    if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;  // tail too small to split
+    {
+        const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
+        p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
+    }
     // smem: resident query tile + as many ring stages as fit
     const int stage_bytes = (kTileN / cg) * 128;
     const int q_bytes = p.kblocks * kQBlockBytes;
     p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - q_bytes) / stage_bytes);
     if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the row-tile ring", idx->dim); return IVR_EUNSUPPORTED; }
     const size_t smem = 1024 + q_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
-    // segments per group and partial-result slots per query tile (mirrors GroupRange on the device)
-    auto g_of = [&](int64_t u) { return static_cast<int>(((u + 1) * p.groups - 1) / Up); };
-    int groups_per_tile = 1;
-    for (int t = 0; t < p.tq; ++t)
-        groups_per_tile = std::max(groups_per_tile, g_of(static_cast<int64_t>(t) * p.ntp + p.ntp - 1) -
-                                                    g_of(static_cast<int64_t>(t) * p.ntp) + 1);
-    const int slots = 2 * groups_per_tile;
-    {
-        const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
-        p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
-    }
+    // segments per group and partial-result slots per query tile (mirrors the device schedule)
+    const int Gl = p.groups - p.g_grid;
+    const int64_t ntl = p.nt - p.ntg, Ul = static_cast<int64_t>(p.tq) * ntl;
+    int left_per_tile = 0;
     p.segs_max = 1;
-    for (int g = 0; g < p.groups; ++g) {
-        const int64_t ub = Up * g / p.groups, ue = Up * (g + 1) / p.groups;
-        if (ue > ub) p.segs_max = std::max(p.segs_max, static_cast<int>((ue - 1) / p.ntp - ub / p.ntp) + 1);
+    if (Gl > 0 && Ul > 0) {
+        auto gl_of = [&](int64_t u) { return static_cast<int>(((u + 1) * Gl - 1) / Ul); };
+        for (int t = 0; t < p.tq; ++t)
+            left_per_tile = std::max(left_per_tile, gl_of(static_cast<int64_t>(t) * ntl + ntl - 1) -
+                                                    gl_of(static_cast<int64_t>(t) * ntl) + 1);
+        for (int g = 0; g < Gl; ++g) {
+            const int64_t ub = Ul * g / Gl, ue = Ul * (g + 1) / Gl;
+            if (ue > ub) p.segs_max = std::max(p.segs_max, static_cast<int>((ue - 1) / ntl - ub / ntl) + 1);
+        }
     }
+    const int slots = 2 * (p.c + left_per_tile);
 
     // workspace carve-up
     size_t off = 0;
@@ -739,8 +731,9 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     p.state = reinterpret_cast<int2*>(ws + o_st);
     p.out_keys = reinterpret_cast<uint64_t*>(ws + o_k);
     p.out_counts = reinterpret_cast<int*>(ws + o_c);
+    const bool timed = idx->timing && first_batch;
 
-    if (idx->timing) cudaEventRecord(idx->ev[4], st);
+    if (timed) cudaEventRecord(idx->ev[4], st);
     {
         const int64_t threads = static_cast<int64_t>(p.nq_pad) * 32;
         queries_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
@@ -749,7 +742,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
         idx->launches[2]++;
         IVR_CUDA(cudaMemsetAsync(p.out_counts, 0, static_cast<size_t>(slots) * p.nq_pad * 4, st));
     }
-    if (idx->timing) cudaEventRecord(idx->ev[5], st);
+    if (timed) cudaEventRecord(idx->ev[5], st);
 
     // TMA descriptors (the row descriptor is cached until the matrix moves or grows)
     CUtensorMap tmq;
@@ -760,13 +753,13 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     }
     const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
 
-    if (idx->timing) cudaEventRecord(idx->ev[0], st);
+    if (timed) cudaEventRecord(idx->ev[0], st);
     int rc;
     if (cg == 2) rc = (kcap == 128) ? launch_mma<2, 8>(tmq, tmx, p, grid, smem, st) : launch_mma<2, 0>(tmq, tmx, p, grid, smem, st);
     else         rc = (kcap == 128) ? launch_mma<1, 8>(tmq, tmx, p, grid, smem, st) : launch_mma<1, 0>(tmq, tmx, p, grid, smem, st);
     IVR_TRY(rc);
     idx->launches[0]++;
-    if (idx->timing) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
+    if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
 
     MergeIn in{};
     in.entries = p.out_keys; in.counts = p.out_counts;
@@ -775,9 +768,23 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     in.n_lists = slots; in.fixed_count = 0;
     IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_t),
                               reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1], q_scale));
-    if (idx->timing) {
+    if (timed) {
         cudaEventRecord(idx->ev[3], st);
         idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
+    }
+    return IVR_OK;
+}
+
+int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+               int64_t id_offset, cudaStream_t st) {
+    // one launch handles at most (#groups) query tiles; larger batches run as several launches
+    // (timing events bracket the first one)
+    const int cg = cta_group_mode();
+    const int64_t per_launch = static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
+    for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
+        const int64_t b = std::min(per_launch, nq - q0);
+        IVR_TRY(search_mma_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k, id_offset, st,
+                                 cg, q0 == 0));
     }
     return IVR_OK;
 }

@@ -108,6 +108,14 @@ def test_mma_adversarial_ties_and_duplicates(cta_group):
     check(idx, ref, base[:20], 100, path=2)
 
 
+def test_mma_more_query_tiles_than_cta_groups(cta_group):
+    """nq beyond one launch's capacity (#CTA groups x tile) runs as several launches."""
+    xb = synth.clip_like(3000, 64, seed=71, n_centres=32)
+    xq = synth.clip_like(19500, 64, seed=72, n_centres=32)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 10, path=2)
+
+
 def test_mma_and_stream_paths_agree():
     xb = synth.clip_like(50_000, 512, seed=67, n_centres=128)
     xq = synth.clip_like(8, 512, seed=68, n_centres=128)
