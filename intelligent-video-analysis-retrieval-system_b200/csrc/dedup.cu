@@ -243,6 +243,126 @@ banded_cosine_g4_kernel(const float* __restrict__ e, int64_t n, int window, floa
     }
 }
 
+// ---------------------------------------------------------------------------
+// Register-window variant (window <= 8, d in {384, 512}) -- the default for those shapes.
+// Every WARP walks its own contiguous run of frames sequentially and keeps the last 8 normalised
+// rows in REGISTERS (the frame loop is unrolled by 8, so the window slot of a frame is a
+// compile-time index).  Frames are prefetched 7 deep with cp.async into a private per-warp staging
+// ring (each lane copies and later reads only its own 16-byte chunks, so no warp or CTA barrier is
+// ever needed).  Per frame: 4-6 LDS.128, 128 x DV/4... FMAs against the register window, one
+// 9-shuffle transpose-reduction of the 8 dot products, one ballot.  No shared-memory ring of
+// normalised rows, no __syncthreads: the kernel is a pure HBM stream.
+// ---------------------------------------------------------------------------
+constexpr int kRwWarps = 4;
+constexpr int kRwSlots = 8;                     // staged frames per warp
+constexpr int kRwWindow = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DV>
+__global__ void __launch_bounds__(kRwWarps * 32, 2)
+banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
+                        uint32_t* __restrict__ masks, float* __restrict__ cos_prev) {
+    extern __shared__ float4 s_stage[];         // [kRwWarps][kRwSlots][DV * 32]
+    constexpr int RS4 = DV * 32;                // float4 per row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kRwWarps + warp;
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * kRwWarps;
+    const int64_t f0 = n * gw / nw, f1 = n * (gw + 1) / nw;
+    if (f0 >= f1) return;                        // no CTA-wide barrier anywhere below
+    const int64_t fs = (f0 - kRwWindow > 0) ? f0 - kRwWindow : 0;
+    float4* stage = s_stage + static_cast<size_t>(warp) * kRwSlots * RS4;
+    const float4* src = reinterpret_cast<const float4*>(e);
+
+    auto issue = [&](int64_t i, int slot) {
+        if (i < f1) {
+#pragma unroll
+            for (int j = 0; j < DV; ++j) cp_async16(stage + slot * RS4 + lane + 32 * j, src + i * RS4 + lane + 32 * j);
+        }
+        cp_async_commit();                      // always commit: keeps the group count uniform
+    };
+#pragma unroll
+    for (int x = 0; x < kRwSlots - 1; ++x) issue(fs + x, x);
+
+    float4 win[kRwWindow][DV];
+#pragma unroll
+    for (int w = 0; w < kRwWindow; ++w)
+#pragma unroll
+        for (int j = 0; j < DV; ++j) win[w][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int64_t i = fs; i < f1; i += kRwWindow) {
+#pragma unroll
+        for (int u = 0; u < kRwWindow; ++u) {
+            const int64_t ii = i + u;
+            if (ii < f1) {                                                  // warp-uniform
+                cp_async_wait<kRwSlots - 2>();                              // frame ii has landed
+                float4 cur[DV];
+#pragma unroll
+                for (int j = 0; j < DV; ++j) cur[j] = stage[u * RS4 + lane + 32 * j];
+                issue(ii + kRwSlots - 1, (u + kRwSlots - 1) % kRwSlots);   // refill the slot read one step ago
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < DV; ++j) {
+                    ss = fmaf(cur[j].x, cur[j].x, ss); ss = fmaf(cur[j].y, cur[j].y, ss);
+                    ss = fmaf(cur[j].z, cur[j].z, ss); ss = fmaf(cur[j].w, cur[j].w, ss);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                float nrm = sqrtf(ss);
+                if (nrm == 0.f) nrm = 1.f;                                  // sklearn: 0 -> 1
+                const float inv = 1.0f / nrm;
+#pragma unroll
+                for (int j = 0; j < DV; ++j) { cur[j].x *= inv; cur[j].y *= inv; cur[j].z *= inv; cur[j].w *= inv; }
+                float acc[kRwWindow];
+#pragma unroll
+                for (int dd = 1; dd <= kRwWindow; ++dd) {
+                    const int w = (u - dd + 2 * kRwWindow) % kRwWindow;     // slot of frame ii - dd
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < DV; ++j) {
+                        a = fmaf(cur[j].x, win[w][j].x, a); a = fmaf(cur[j].y, win[w][j].y, a);
+                        a = fmaf(cur[j].z, win[w][j].z, a); a = fmaf(cur[j].w, win[w][j].w, a);
+                    }
+                    acc[dd - 1] = a;
+                }
+#pragma unroll
+                for (int j = 0; j < DV; ++j) win[u][j] = cur[j];            // frame ii replaces frame ii - 8
+                // transpose-reduce 8 sums over 32 lanes: lane l ends with the total of index l >> 2
+#pragma unroll
+                for (int s = 16, half = 4; half > 0; s >>= 1, half >>= 1) {
+                    const bool up = (lane & s) != 0;
+#pragma unroll
+                    for (int a = 0; a < half; ++a) {
+                        const float send = up ? acc[a] : acc[a + half];
+                        const float keep = up ? acc[a + half] : acc[a];
+                        acc[a] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                    }
+                }
+                float val = acc[0];
+                val += __shfl_xor_sync(0xffffffffu, val, 2);
+                val += __shfl_xor_sync(0xffffffffu, val, 1);
+                const int dd = (lane >> 2) + 1;
+                const bool ge = dd <= window && ii - dd >= 0 && val >= thr;
+                const unsigned ballot = __ballot_sync(0xffffffffu, ge);
+                if (ii >= f0 && lane == 0) {
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int b = 0; b < kRwWindow; ++b) m |= ((ballot >> (4 * b)) & 1u) << b;
+                    if (masks) masks[ii] = m;
+                    if (cos_prev) cos_prev[ii] = (ii >= 1) ? val : 1.0f;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // One thread per scene: the reference's greedy rule on the bit masks.
 //   keep_i = !exists d in [1, min(window, i - scene_start)] : keep_{i-d} && bit_{d-1}(mask_i)
 __global__ void window_resolve_kernel(const uint32_t* __restrict__ masks,
@@ -328,8 +448,28 @@ int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, u
                   float* cos_prev, int sm_count, cudaStream_t st) {
     if (n <= 0) return IVR_OK;
     const bool aligned = (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0;
-    // register-tiled kernel: window <= 8, d = 384 or 512 (IVR_DEDUP_SIMPLE=1 forces the generic one)
-    if (aligned && window <= kG4Window && (d == 512 || d == 384) && !env_flag("IVR_DEDUP_SIMPLE", 0)) {
+    // IVR_DEDUP_KERNEL: 0 = register-window kernel (default for window <= 8, d = 384/512),
+    //                   1 = shared-ring 4-frames-per-warp kernel, 2 = generic kernel
+    const int variant = env_flag("IVR_DEDUP_KERNEL", 0);
+    if (aligned && window <= kRwWindow && (d == 512 || d == 384) && variant == 0) {
+        const size_t smem = static_cast<size_t>(kRwWarps) * kRwSlots * d * sizeof(float);
+        int64_t grid = static_cast<int64_t>(sm_count) * 2;                  // persistent: 2 CTAs per SM
+        const int64_t max_grid = (n + 255) / 256;
+        if (grid > max_grid) grid = max_grid;
+        if (grid < 1) grid = 1;
+        if (d == 512) {
+            auto kern = banded_cosine_rw_kernel<4>;
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+        } else {
+            auto kern = banded_cosine_rw_kernel<3>;
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+        }
+        IVR_CUDA(cudaGetLastError());
+        return IVR_OK;
+    }
+    if (aligned && window <= kG4Window && (d == 512 || d == 384) && variant == 1) {
         const size_t smem = static_cast<size_t>(kG4Ring) * d * sizeof(float);
         int64_t grid = static_cast<int64_t>(sm_count) * 4;
         const int64_t max_grid = (n + 127) / 128;

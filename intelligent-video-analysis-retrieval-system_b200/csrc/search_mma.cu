@@ -256,6 +256,7 @@ struct MmaParams {
     int     c;               // grid groups per query tile
     int     g_grid;          // c * tq groups walk rows [0, ntg) in lockstep
     int64_t ntg;             // row tiles of the grid part; the leftover groups own [ntg, nt)
+    int     stagger;         // grid part: query tile t starts `stagger * t` steps into its row walk
     int     groups;          // CTA groups in the launch
     int     nq_pad;          // tq * 128 * CG
     int     segs_max;        // max query tiles one group touches
@@ -293,8 +294,15 @@ __device__ __forceinline__ void for_each_unit(const MmaParams& p, int group, FV&
         const int t = group % p.tq, i = group / p.tq;
         if (i >= p.ntg) return;
         f_visit(0, t, true, 0);
-        int64_t n = 0;
-        for (int64_t j = i; j < p.ntg; j += p.c, ++n) f_unit(0, t, j, n);
+        // Query tile t runs `stagger * t` steps ahead (cyclically): the Tq groups that share a row
+        // tile request it a step apart instead of in the same instant, so the first request has
+        // filled L2 by the time the others arrive.
+        const int64_t nsteps = (p.ntg - i + p.c - 1) / p.c;
+        int64_t m = (static_cast<int64_t>(p.stagger) * t) % nsteps;
+        for (int64_t n = 0; n < nsteps; ++n) {
+            f_unit(0, t, i + m * p.c, n);
+            if (++m == nsteps) m = 0;
+        }
         f_visit_end(0, t, 0, true);
     } else {
         const LeftRange lr(p, group);
@@ -682,6 +690,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     p.g_grid = p.c * p.tq;
     p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
     if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;  // tail too small to split
+    p.stagger = std::max(0, env_int("IVR_MMA_STAGGER", 1));
     {
         const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
