@@ -66,6 +66,7 @@ struct MergeIn {
     int64_t cnt_list_stride, cnt_q_stride;
     int     n_lists;
     int     fixed_count;
+    int     raw;             // entries are raw {score bits, row} pairs (converted to keys on load)
 };
 // final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset;
 // scores are multiplied by q_scale[q] when q_scale != nullptr (power-of-two query scaling)

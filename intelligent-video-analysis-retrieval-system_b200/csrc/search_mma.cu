@@ -392,6 +392,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
             },
             [&](int, int, int, bool) { if (pending_q) load_q(); });
+        // consumed every q_empty completion but the last, in order: wait for the last one so that no
+        // asynchronous arrive can land after the CTA has retired
+        if (nload > 0) mbar_wait(q_empty, (nload - 1) & 1);
     } else if (warp == 1 && lane == 0) {
         // ============================ MMA issuer (leader CTA) =================
         // q_empty ("the MMAs reading the query tile have retired") is committed at the end of a visit
@@ -433,7 +436,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     ++ncommit;
                 }
             });
-        if (ncommit > 0) mbar_wait(q_empty, (ncommit - 1) & 1);
+        (void)ncommit;
     } else if (warp >= 4) {
         // ============================ epilogue: fused top-k ====================
         const int set = (warp - 4) >> 2;                           // accumulator / list set 0 or 1
@@ -585,6 +588,246 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
 }
 
+
+// ===================================================================================
+// Row-tile-resident variant (cta_group::2 only), used for large query batches.
+//
+// Profiling the query-tile-resident kernel at 4096 queries showed the L2 slices 99 % busy and
+// every query tile re-fetching the rows from HBM (13x the algorithmic traffic, no schedule --
+// phases, lockstep, stagger, eviction hints -- changed that; see profiles/).  Here the roles are
+// swapped: a CTA pair keeps one ROW tile (256 rows x dpad, 128 KB per CTA) resident in shared
+// memory and streams the QUERY tiles past it through the TMA ring.  The query matrix is a few MB
+// and stays hot in L2, every row of the shard is fetched from HBM exactly ONCE per search, and the
+// row tiles are simply split evenly over the pairs (no lockstep needed).  The accumulator is still
+// [queries x rows], so the epilogue is unchanged except that a thread's query changes with every
+// unit: its list / count live in per-(pair, set, query) arrays, its threshold is the per-query
+// threshold shared by all CTAs, and the lists are folded directly by the merge kernel (no flush).
+// ===================================================================================
+struct XresParams {
+    int64_t n_rows;
+    int     nq, k, C, kblocks, stages, tq;
+    int64_t nt;              // row tiles
+    int     groups;          // CTA pairs
+    int     nq_pad;          // tq * 256
+    uint64_t* lists;         // [groups][2 sets][nq_pad][C] raw candidate lists
+    int*      counts;        // [groups][2 sets][nq_pad]
+    uint32_t* tau_g;         // [nq_pad] shared per-query threshold (order-preserving encoding)
+    uint64_t  row_policy;
+};
+
+template <int E>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                       const XresParams p) {
+    constexpr int CG = 2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int group = blockIdx.x / CG;
+
+    constexpr uint32_t stage_bytes = kTileQ * 128;               // one query k-block per CTA: 16 KB
+    const uint32_t x_bytes = p.kblocks * kQBlockBytes;           // this CTA's half of the row tile
+    const uint32_t smem_x = smem_base;
+    const uint32_t smem_s = smem_x + x_bytes;
+    const uint32_t bars = smem_s + p.stages * stage_bytes;
+    auto full_bar  = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (16 + s); };
+    const uint32_t x_full = bars + 8u * 32, x_empty = bars + 8u * 33;
+    auto tfull_bar  = [&](int a) { return bars + 8u * (34 + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (36 + a); };
+    const uint32_t tmem_slot = bars + 8u * 40;
+
+    const int64_t j0 = p.nt * group / p.groups, j1 = p.nt * (group + 1) / p.groups;   // owned row tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_x); }
+    if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0 && lane == 0) {
+        // ============================ TMA producer ============================
+        int stage = 0; uint32_t phase = 0; int nload = 0;
+        for (int64_t j = j0; j < j1; ++j) {
+            bool pending = true; int issued = 0;
+            auto load_x = [&]() {
+                if (nload > 0) mbar_wait(x_empty, (nload - 1) & 1);  // MMAs finished with the old row tile
+                if (cta_rank == 0) mbar_expect_tx(x_full, x_bytes * CG);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_2d<CG>(smem_x + kb * kQBlockBytes, &tmap_x, x_full, kb * kKBlock,
+                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kTileQ, p.row_policy);
+                ++nload;
+                pending = false;
+            };
+            if (nload == 0) load_x();
+            for (int t = 0; t < p.tq; ++t) {
+                if (t == p.tq / 2 && j + 1 < j1) {
+                    // pull the next row tile into L2 while this one is being used
+                    for (int kb = 0; kb < p.kblocks; ++kb)
+                        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(kb * kKBlock),
+                                       "r"(static_cast<int>((j + 1) * kTileN) + static_cast<int>(cta_rank) * kTileQ)
+                                     : "memory");
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    if (pending && issued >= p.stages) load_x();     // ring refilled first, then the row tile
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_bytes * CG);
+                    tma_load_2d<CG>(smem_s + stage * stage_bytes, &tmap_q, full_bar(stage), kb * kKBlock,
+                                    t * (kTileQ * CG) + static_cast<int>(cta_rank) * kTileQ, kL2EvictLast);
+                    ++issued;
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (pending) load_x();
+        }
+        // This thread consumed every x_empty completion but the last, in order: waiting for the last
+        // one here is unambiguous and keeps the CTA alive until no asynchronous arrive is in flight.
+        if (nload > 0) mbar_wait(x_empty, (nload - 1) & 1);
+    } else if (warp == 1 && lane == 0) {
+        // ============================ MMA issuer (leader CTA) =================
+        constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
+        int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0; int64_t n = 0;
+        for (int64_t j = j0; j < j1; ++j) {
+            if (cta_rank == 0) mbar_wait(x_full, nload & 1);
+            ++nload;
+            if (cta_rank == 0) {
+                for (int t = 0; t < p.tq; ++t, ++n) {
+                    const int acc = static_cast<int>(n & 1);
+                    const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_s + stage * stage_bytes;       // A: streamed query k-block
+                        const uint32_t b0 = smem_x + kb * kQBlockBytes;         // B: resident row-tile k-block
+#pragma unroll
+                        for (int k4 = 0; k4 < kKBlock / 16; ++k4)
+                            umma_f16<CG>(tmem_d, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
+                                         (kb | k4) ? 1u : 0u);
+                        umma_commit<CG>(empty_bar(stage));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit<CG>(tfull_bar(acc));
+                }
+                umma_commit<CG>(x_empty);                           // row tile released when its MMAs retire
+            }
+            ++ncommit;
+        }
+        (void)ncommit;
+    } else if (warp >= 4) {
+        // ============================ epilogue: fused top-k ====================
+        const int set = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const float POS_INF = __int_as_float(0x7f800000);
+        const int64_t set_base = (static_cast<int64_t>(group) * 2 + set) * p.nq_pad;
+        int cnt = 0; float tau = 0.f; int64_t q_global = 0; bool q_ok = false;
+        uint64_t* my_list = nullptr; uint64_t* warp_lists = nullptr;
+        // state of this set's NEXT unit, prefetched while the current one is processed
+        int64_t pf_n = -1; int pf_cnt = 0; uint32_t pf_tau = 0;
+        auto q_of = [&](int t) { return static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r; };
+
+        auto compact_lane = [&](int l) {
+            const int c_l = __shfl_sync(0xffffffffu, cnt, l);
+            __syncwarp();
+            const float t_l = warp_compact_raw<E>(warp_lists + static_cast<int64_t>(l) * p.C, c_l, p.k, p.C, lane);
+            if (lane == l) {
+                cnt = min(cnt, p.k);
+                if (t_l > tau) tau = t_l;
+                if (q_ok && cnt >= p.k) atomicMax(p.tau_g + q_global, f2ord(t_l));
+            }
+        };
+        auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
+            float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+            for (int i = 2; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            if (!__any_sync(0xffffffffu, m > tau)) return;
+            const uint32_t rowc = static_cast<uint32_t>(row0) + c * 32;
+            if (nvalid == kTileN) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float sc = __uint_as_float(v[i]);
+                    uint64_t* dst = my_list + cnt;
+                    asm volatile(
+                        "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
+                        "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
+                        ::"f"(sc), "f"(tau), "l"(dst), "r"(v[i]), "r"(rowc + i) : "memory");
+                    cnt += (sc > tau) ? 1 : 0;
+                }
+            } else {
+                for (int i = 0; i < 32; ++i) {
+                    const float sc = __uint_as_float(v[i]);
+                    if (sc > tau && c * 32 + i < nvalid) {
+                        my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
+                        ++cnt;
+                    }
+                }
+            }
+        };
+
+        const int64_t n_units = (j1 - j0) * p.tq;
+        for (int64_t n = set; n < n_units; n += 2) {
+            const int64_t j = j0 + n / p.tq;
+            const int t = static_cast<int>(n % p.tq);
+            q_global = q_of(t);
+            q_ok = q_global < p.nq;
+            const int64_t idx = set_base + q_global;
+            if (pf_n == n) { cnt = pf_cnt; tau = ord2f(pf_tau); }
+            else { cnt = p.counts[idx]; tau = ord2f(__ldcg(p.tau_g + q_global)); }
+            if (!q_ok) tau = POS_INF;                               // padded queries admit nothing
+            my_list = p.lists + idx * p.C;
+            warp_lists = my_list - static_cast<int64_t>(lane) * p.C;
+            if (n + 2 < n_units) {                                  // prefetch the state of unit n + 2
+                const int64_t q2 = q_of(static_cast<int>((n + 2) % p.tq));
+                pf_n = n + 2; pf_cnt = p.counts[set_base + q2]; pf_tau = __ldcg(p.tau_g + q2);
+            }
+            const int64_t row0 = j * kTileN;
+            const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
+            mbar_wait(tfull_bar(set), static_cast<uint32_t>((n >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(set * kTileN);
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+            for (int c = 0; c < kTileN / 32; c += 2) {
+                unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
+                while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
+                tmem_wait_ld(va);
+                tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                process_chunk(va, c, row0, nvalid);
+                tmem_wait_ld(vb);
+                if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                process_chunk(vb, c + 1, row0, nvalid);
+            }
+            p.counts[idx] = cnt;
+            // the same query comes back when the next row tile is swept; when tq is odd the prefetched
+            // count of unit n + 2 could be this very slot only if tq == 2 -- excluded: tq == 2 => n + 2 has the same t
+            if (pf_n == n + 2 && static_cast<int>((n + 2) % p.tq) == t) pf_cnt = cnt;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(set), 0);
+        }
+    }
+
+    // ------------------------------------------------------------------ teardown ----
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
 // fp32 [nq, dim] -> fp16 [nq_pad, dpad] (zero padded), one warp per query.  Each query is scaled by
 // a power of two so that its largest component lies in [0.5, 1): exact, keeps fp16 in range for
 // any query norm, and is undone on the final scores (scale[q]).
@@ -646,8 +889,9 @@ static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
 }
-// IVR_MMA_CTA_GROUP=2 selects the cta_group::2 (CTA pair) variant; read per call so tests can flip it
-static int cta_group_mode() { return env_int("IVR_MMA_CTA_GROUP", 1) == 2 ? 2 : 1; }
+// IVR_MMA_CTA_GROUP=1 selects the single-CTA variant of the query-tile-resident kernel (default: CTA pairs,
+// cta_group::2); read per call so tests can flip it
+static int cta_group_mode() { return env_int("IVR_MMA_CTA_GROUP", 2) == 1 ? 1 : 2; }
 
 bool mma_supported(const ivr_index* idx, int64_t nq, int k) {
     (void)nq;
@@ -784,11 +1028,125 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     return IVR_OK;
 }
 
+
+// Row-tile-resident path: cta_group::2, any number of query tiles.
+static int search_mma_xres_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                                 int64_t id_offset, cudaStream_t st, bool first_batch) {
+    constexpr int cg = 2;
+    const int kcap = kcap_for(k);
+    const int C = 2 * kcap;
+    const int mq = kTileQ * cg;
+    XresParams p{};
+    p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.k = k; p.C = C;
+    p.kblocks = idx->dpad / kKBlock;
+    p.tq = static_cast<int>((nq + mq - 1) / mq);
+    p.nt = (idx->ntotal + kTileN - 1) / kTileN;
+    p.nq_pad = p.tq * mq;
+    int grid = idx->sm_count / cg * cg;
+    p.groups = grid / cg;
+    if (p.nt < p.groups) { p.groups = static_cast<int>(p.nt); grid = p.groups * cg; }
+    {
+        const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
+        p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
+    }
+    const int stage_bytes = kTileQ * 128;
+    const int x_bytes = p.kblocks * kQBlockBytes;
+    p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - x_bytes) / stage_bytes);
+    if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the query ring", idx->dim); return IVR_EUNSUPPORTED; }
+    const size_t smem = 1024 + x_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
+    const int n_lists = p.groups * 2;
+
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_q  = carve(static_cast<size_t>(p.nq_pad) * idx->dpad * 2);
+    const size_t o_sc = carve(static_cast<size_t>(p.nq_pad) * 4);
+    const size_t o_tg = carve(static_cast<size_t>(p.nq_pad) * 4);
+    const size_t o_l  = carve(static_cast<size_t>(n_lists) * p.nq_pad * C * 8);
+    const size_t o_c  = carve(static_cast<size_t>(n_lists) * p.nq_pad * 4);
+    const size_t tmp_keys = merge_tmp_entries(n_lists, nq, k);
+    const size_t o_t  = carve(tmp_keys * 8);
+    const size_t o_tc = carve((static_cast<size_t>(n_lists) * nq + 64) * 4);
+    IVR_TRY(ensure_ws(idx, off));
+    char* ws = static_cast<char*>(idx->ws);
+    __half* q_h = reinterpret_cast<__half*>(ws + o_q);
+    float* q_scale = reinterpret_cast<float*>(ws + o_sc);
+    p.tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
+    p.lists = reinterpret_cast<uint64_t*>(ws + o_l);
+    p.counts = reinterpret_cast<int*>(ws + o_c);
+    const bool timed = idx->timing && first_batch;
+
+    if (timed) cudaEventRecord(idx->ev[4], st);
+    {
+        const int64_t threads = static_cast<int64_t>(p.nq_pad) * 32;
+        queries_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+            q_dev, q_h, q_scale, p.tau_g, nq, p.nq_pad, idx->dim, idx->dpad);
+        IVR_CUDA(cudaGetLastError());
+        idx->launches[2]++;
+        IVR_CUDA(cudaMemsetAsync(p.counts, 0, static_cast<size_t>(n_lists) * p.nq_pad * 4, st));
+    }
+    if (timed) cudaEventRecord(idx->ev[5], st);
+
+    CUtensorMap tmq;
+    IVR_TRY(make_tmap(&tmq, q_h, p.nq_pad, idx->dpad, kTileQ));
+    if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != kTileN / cg) {
+        IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, kTileN / cg));
+        idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = kTileN / cg;
+    }
+    const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
+
+    if (timed) cudaEventRecord(idx->ev[0], st);
+    {
+        auto launch = [&](auto kern) -> int {
+            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(static_cast<unsigned>(grid));
+            cfg.blockDim = dim3(kMmaThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            IVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmq, tmx, p));
+            return IVR_OK;
+        };
+        IVR_TRY(kcap == 128 ? launch(search_mma_xres_kernel<8>) : launch(search_mma_xres_kernel<0>));
+    }
+    idx->launches[0]++;
+    if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
+
+    MergeIn in{};
+    in.entries = p.lists; in.counts = p.counts;
+    in.list_stride = static_cast<int64_t>(p.nq_pad) * C; in.q_stride = C;
+    in.cnt_list_stride = p.nq_pad; in.cnt_q_stride = 1;
+    in.n_lists = n_lists; in.fixed_count = 0; in.raw = 1;
+    IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_t),
+                              reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1], q_scale));
+    if (timed) {
+        cudaEventRecord(idx->ev[3], st);
+        idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
+    }
+    return IVR_OK;
+}
+
 int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                int64_t id_offset, cudaStream_t st) {
-    // one launch handles at most (#groups) query tiles; larger batches run as several launches
-    // (timing events bracket the first one)
-    const int cg = cta_group_mode();
+    // Mode selection: IVR_MMA_MODE = 0 auto, 1 query-tile-resident, 2 row-tile-resident.
+    // Auto: the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up.
+    const int mode = env_int("IVR_MMA_MODE", 0);
+    const int cg_env = cta_group_mode();
+    const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2);
+    if (xres) {
+        const int64_t per_launch = 16384;                          // bounds the candidate-list workspace
+        for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
+            const int64_t b = std::min(per_launch, nq - q0);
+            IVR_TRY(search_mma_xres_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k,
+                                          id_offset, st, q0 == 0));
+        }
+        return IVR_OK;
+    }
+    // query-tile-resident: one launch handles at most (#groups) query tiles
+    const int cg = cg_env;
     const int64_t per_launch = static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
     for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
         const int64_t b = std::min(per_launch, nq - q0);

@@ -33,7 +33,8 @@ __device__ __forceinline__ void for_each_key(const MergeIn& in, int64_t q, int l
                                   : in.fixed_count;
         const uint64_t* base = in.entries + l * in.list_stride + q * in.q_stride;
         for (int i = lane; i < cnt; i += 32) {
-            const uint64_t key = base[i];
+            uint64_t key = base[i];
+            if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
             if (key != 0ull) f(key);
         }
     }
@@ -170,7 +171,7 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
         nx.entries = ebuf; nx.counts = cbuf;
         nx.list_stride = nq * k; nx.q_stride = k;
         nx.cnt_list_stride = nq; nx.cnt_q_stride = 1;
-        nx.n_lists = groups; nx.fixed_count = 0;
+        nx.n_lists = groups; nx.fixed_count = 0; nx.raw = 0;
         ebuf += static_cast<size_t>(groups) * nq * k;
         cbuf += static_cast<size_t>(groups) * nq;
         in = nx;

@@ -54,9 +54,12 @@ def test_stream_path_k_values(k):
     check(idx, ref, xq, k, path=1)
 
 
-@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_group2"])
+@pytest.fixture(params=[(1, 1), (2, 1), (2, 2)], ids=["qres_cta_group1", "qres_cta_group2", "xres_cta_group2"])
 def cta_group(request, monkeypatch):
-    monkeypatch.setenv("IVR_MMA_CTA_GROUP", str(request.param))
+    """Kernel variants of the tcgen05 path: query-tile-resident (1 CTA / CTA pair), row-tile-resident."""
+    cg, mode = request.param
+    monkeypatch.setenv("IVR_MMA_CTA_GROUP", str(cg))
+    monkeypatch.setenv("IVR_MMA_MODE", str(mode))
     return request.param
 
 

@@ -38,6 +38,7 @@ def probe(n, d, nq, k, cg):
 if __name__ == "__main__":
     cgs = [int(a) for a in sys.argv[1:]] or [1]
     for cg in cgs:
+        print(f"--- cta_group={cg} IVR_MMA_MODE={os.environ.get('IVR_MMA_MODE', '0')}", flush=True)
         probe(1000, 64, 8, 10, cg)
         probe(5000, 128, 130, 100, cg)
         probe(100_000, 512, 1000, 100, cg)
