@@ -306,19 +306,15 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
 #pragma unroll
                 for (int j = 0; j < DV; ++j) cur[j] = stage[u * RS4 + lane + 32 * j];
                 issue(ii + kRwSlots - 1, (u + kRwSlots - 1) % kRwSlots);   // refill the slot read one step ago
+                // The 8 dot products are taken with the RAW row and scaled by 1/||row|| afterwards
+                // (dot(x/|x|, w) == dot(x, w)/|x| up to one rounding), so the norm reduction and the
+                // dot reduction are two independent shuffle chains instead of one long one.
                 float ss = 0.f;
 #pragma unroll
                 for (int j = 0; j < DV; ++j) {
                     ss = fmaf(cur[j].x, cur[j].x, ss); ss = fmaf(cur[j].y, cur[j].y, ss);
                     ss = fmaf(cur[j].z, cur[j].z, ss); ss = fmaf(cur[j].w, cur[j].w, ss);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                float nrm = sqrtf(ss);
-                if (nrm == 0.f) nrm = 1.f;                                  // sklearn: 0 -> 1
-                const float inv = 1.0f / nrm;
-#pragma unroll
-                for (int j = 0; j < DV; ++j) { cur[j].x *= inv; cur[j].y *= inv; cur[j].z *= inv; cur[j].w *= inv; }
                 float acc[kRwWindow];
 #pragma unroll
                 for (int dd = 1; dd <= kRwWindow; ++dd) {
@@ -332,7 +328,7 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
                     acc[dd - 1] = a;
                 }
 #pragma unroll
-                for (int j = 0; j < DV; ++j) win[u][j] = cur[j];            // frame ii replaces frame ii - 8
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 // transpose-reduce 8 sums over 32 lanes: lane l ends with the total of index l >> 2
 #pragma unroll
                 for (int s = 16, half = 4; half > 0; s >>= 1, half >>= 1) {
@@ -347,6 +343,15 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
                 float val = acc[0];
                 val += __shfl_xor_sync(0xffffffffu, val, 2);
                 val += __shfl_xor_sync(0xffffffffu, val, 1);
+                float nrm = sqrtf(ss);
+                if (nrm == 0.f) nrm = 1.f;                                  // sklearn: 0 -> 1
+                const float inv = 1.0f / nrm;
+                val *= inv;
+#pragma unroll
+                for (int j = 0; j < DV; ++j) {                              // frame ii (normalised) replaces frame ii - 8
+                    win[u][j].x = cur[j].x * inv; win[u][j].y = cur[j].y * inv;
+                    win[u][j].z = cur[j].z * inv; win[u][j].w = cur[j].w * inv;
+                }
                 const int dd = (lane >> 2) + 1;
                 const bool ge = dd <= window && ii - dd >= 0 && val >= thr;
                 const unsigned ballot = __ballot_sync(0xffffffffu, ge);

@@ -244,6 +244,48 @@ __device__ __forceinline__ float warp_compact_raw(uint64_t* list, int cnt, int k
     }
 }
 
+
+// One 32-column chunk of one query's scores (v) against its admission threshold.  Sub-maxima of
+// the four 8-column groups are formed with independent 3-input max trees (short dependency
+// chains); a warp vote per group skips groups without survivors, so the common "one survivor in
+// the whole warp-chunk" case costs 8 predicated stores instead of 32.
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float tau, int& cnt, uint64_t* my_list,
+                                             uint32_t rowc, int col0, int nvalid) {
+    float g8[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float a = fmaxf(fmaxf(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+        const float b = fmaxf(fmaxf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+        g8[g] = fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+    }
+    const float m = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
+    if (!__any_sync(0xffffffffu, m > tau)) return;
+    if (nvalid == kTileN) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, g8[g] > tau)) continue;       // warp-uniform
+#pragma unroll
+            for (int i = 8 * g; i < 8 * g + 8; ++i) {                  // branch-free: predicated 8-byte store
+                const float sc = __uint_as_float(v[i]);
+                uint64_t* dst = my_list + cnt;
+                asm volatile(
+                    "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
+                    "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
+                    ::"f"(sc), "f"(tau), "l"(dst), "r"(v[i]), "r"(rowc + i) : "memory");
+                cnt += (sc > tau) ? 1 : 0;
+            }
+        }
+    } else {                                                            // last, partial row tile of the shard
+        for (int i = 0; i < 32; ++i) {
+            const float sc = __uint_as_float(v[i]);
+            if (sc > tau && col0 + i < nvalid) {
+                my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
+                ++cnt;
+            }
+        }
+    }
+}
+
 struct MmaParams {
     int64_t n_rows;          // rows in this shard
     int     nq;              // real queries
@@ -261,6 +303,7 @@ struct MmaParams {
     int     nq_pad;          // tq * 128 * CG
     int     segs_max;        // max query tiles one group touches
     uint64_t row_policy;     // L2 eviction priority of the row-tile loads
+    int      skip_epilogue;  // debug/perf probe: drain nothing (results are garbage)
     uint64_t* lists;         // [grid CTAs][segs_max][2 sets][128][C] raw candidate lists
     int2*     state;         // [grid CTAs][segs_max][2 sets][128] {cnt, tau bits}
     uint32_t* tau_g;         // [nq_pad] order-preserving encoding of the shared per-query threshold
@@ -465,32 +508,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
-            // three-input max tree, then a warp vote: most chunks have no survivor
-            float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-#pragma unroll
-            for (int i = 2; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-            if (!__any_sync(0xffffffffu, m > tau)) return;
-            const uint32_t rowc = static_cast<uint32_t>(row0) + c * 32;
-            if (nvalid == kTileN) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {                      // branch-free: predicated 8-byte store
-                    const float sc = __uint_as_float(v[i]);
-                    uint64_t* dst = my_list + cnt;
-                    asm volatile(
-                        "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
-                        "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
-                        ::"f"(sc), "f"(tau), "l"(dst), "r"(v[i]), "r"(rowc + i) : "memory");
-                    cnt += (sc > tau) ? 1 : 0;
-                }
-            } else {                                                // last, partial row tile of the shard
-                for (int i = 0; i < 32; ++i) {
-                    const float sc = __uint_as_float(v[i]);
-                    if (sc > tau && c * 32 + i < nvalid) {
-                        my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
-                        ++cnt;
-                    }
-                }
-            }
+            filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
         };
 
         for_each_unit(p, group,
@@ -517,9 +535,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(set * kTileN);
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
+                if (!p.skip_epilogue) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < kTileN / 32; c += 2) {
+                for (int c = 0; c < (p.skip_epilogue ? 0 : kTileN / 32); c += 2) {
                     // make room: two chunks can add up to 64 entries to one list
                     unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
                     while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
@@ -613,6 +631,7 @@ struct XresParams {
     int*      counts;        // [groups][2 sets][nq_pad]
     uint32_t* tau_g;         // [nq_pad] shared per-query threshold (order-preserving encoding)
     uint64_t  row_policy;
+    int       skip_epilogue;   // debug/perf probe: drain nothing (results are garbage)
 };
 
 template <int E>
@@ -750,37 +769,15 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             }
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
-            float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-#pragma unroll
-            for (int i = 2; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-            if (!__any_sync(0xffffffffu, m > tau)) return;
-            const uint32_t rowc = static_cast<uint32_t>(row0) + c * 32;
-            if (nvalid == kTileN) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float sc = __uint_as_float(v[i]);
-                    uint64_t* dst = my_list + cnt;
-                    asm volatile(
-                        "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
-                        "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
-                        ::"f"(sc), "f"(tau), "l"(dst), "r"(v[i]), "r"(rowc + i) : "memory");
-                    cnt += (sc > tau) ? 1 : 0;
-                }
-            } else {
-                for (int i = 0; i < 32; ++i) {
-                    const float sc = __uint_as_float(v[i]);
-                    if (sc > tau && c * 32 + i < nvalid) {
-                        my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
-                        ++cnt;
-                    }
-                }
-            }
+            filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
         };
 
         const int64_t n_units = (j1 - j0) * p.tq;
+        // (j, t) of unit n advance by two units per iteration without divisions
+        int64_t j = j0 + set / p.tq;
+        int t = set % p.tq;
+        const int step_j = 2 / p.tq, step_t = 2 % p.tq;
         for (int64_t n = set; n < n_units; n += 2) {
-            const int64_t j = j0 + n / p.tq;
-            const int t = static_cast<int>(n % p.tq);
             q_global = q_of(t);
             q_ok = q_global < p.nq;
             const int64_t idx = set_base + q_global;
@@ -789,8 +786,10 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             if (!q_ok) tau = POS_INF;                               // padded queries admit nothing
             my_list = p.lists + idx * p.C;
             warp_lists = my_list - static_cast<int64_t>(lane) * p.C;
+            int t2 = t + step_t; int64_t j2 = j + step_j;
+            if (t2 >= p.tq) { t2 -= p.tq; ++j2; }
             if (n + 2 < n_units) {                                  // prefetch the state of unit n + 2
-                const int64_t q2 = q_of(static_cast<int>((n + 2) % p.tq));
+                const int64_t q2 = q_of(t2);
                 pf_n = n + 2; pf_cnt = p.counts[set_base + q2]; pf_tau = __ldcg(p.tau_g + q2);
             }
             const int64_t row0 = j * kTileN;
@@ -800,9 +799,9 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(set * kTileN);
             uint32_t va[32], vb[32];
-            tmem_ld_32x32(taddr, va);
+            if (!p.skip_epilogue) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; c += 2) {
+            for (int c = 0; c < (p.skip_epilogue ? 0 : kTileN / 32); c += 2) {
                 unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
                 while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
                 tmem_wait_ld(va);
@@ -815,10 +814,11 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             p.counts[idx] = cnt;
             // the same query comes back when the next row tile is swept; when tq is odd the prefetched
             // count of unit n + 2 could be this very slot only if tq == 2 -- excluded: tq == 2 => n + 2 has the same t
-            if (pf_n == n + 2 && static_cast<int>((n + 2) % p.tq) == t) pf_cnt = cnt;
+            if (pf_n == n + 2 && t2 == t) pf_cnt = cnt;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(set), 0);
+            t = t2; j = j2;
         }
     }
 
@@ -935,6 +935,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
     if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;  // tail too small to split
     p.stagger = std::max(0, env_int("IVR_MMA_STAGGER", 1));
+    p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
     {
         const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
@@ -1046,6 +1047,7 @@ static int search_mma_xres_batch(ivr_index* idx, const float* q_dev, int64_t nq,
     p.groups = grid / cg;
     if (p.nt < p.groups) { p.groups = static_cast<int>(p.nt); grid = p.groups * cg; }
     {
+        p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
         const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
     }
