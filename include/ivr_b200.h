@@ -50,7 +50,7 @@ extern "C" {
 
 /* search path selector for ivr_index_search*(): */
 #define IVR_PATH_AUTO    0
-#define IVR_PATH_STREAM  1    /* K3: SIMT streaming, <= 4 queries per pass, HBM-bound          */
+#define IVR_PATH_STREAM  1    /* K3: SIMT streaming, <= 4 queries per pass, HBM-bound (auto: nq <= 2) */
 #define IVR_PATH_MMA     2    /* K1+K2: tcgen05/TMEM batched GEMM with fused top-k epilogue   */
 
 typedef struct ivr_index ivr_index;
@@ -66,7 +66,8 @@ IVR_API int         ivr_device_info(int device, char* name, size_t name_len, int
 /* ---- flat inner-product index ------------------------------------------
  * Replaces faiss.IndexFlatIP(dim) + .add + .ntotal + .reset
  *   (unified_index.py:1767, 1779; core.py:1208, 827, 843, 268).
- * Rows are stored row-major in HBM as bf16 (dim padded to a multiple of 64);
+ * Rows are stored row-major in HBM as fp16 (dim padded to a multiple of 64;
+ * values are saturated to +-65504 -- the reference only adds L2-normalised rows);
  * ids are the insertion order 0..ntotal-1.
  */
 IVR_API int     ivr_index_create(int dim, int device, ivr_index** out);

@@ -294,7 +294,8 @@ struct MmaParams {
     int     kblocks;         // dpad / 64
     int     stages;          // row-tile ring depth
     int     tq;              // query tiles
-    int64_t nt;              // row tiles
+    int64_t nt;              // row tiles of this launch
+    int64_t tile0;           // first row tile of this launch (row id = (tile0 + j) * 256 + column)
     int     c;               // grid groups per query tile
     int     g_grid;          // c * tq groups walk rows [0, ntg) in lockstep
     int64_t ntg;             // row tiles of the grid part; the leftover groups own [ntg, nt)
@@ -428,7 +429,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (cta_rank == 0) mbar_expect_tx(full_bar(stage), stage_bytes * CG);
                     tma_load_2d<CG>(smem_b + stage * stage_bytes, &tmap_x, full_bar(stage), kb * kKBlock,
-                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta,
+                                    static_cast<int>((p.tile0 + j) * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta,
                                     p.row_policy);
                     ++issued_since;
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -508,6 +509,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
+            if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
             filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
         };
 
@@ -525,7 +527,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             [&](int, int, int64_t j, int64_t n) {
                 if (static_cast<int>(n & 1) != set) return;
                 const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
-                const int64_t row0 = j * kTileN;
+                const int64_t row0 = (p.tile0 + j) * kTileN;
                 const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
                 // the threshold shared by all CTAs: issue the load now, fold it in after this tile
                 // (its L2 latency hides behind the chunk loop)
@@ -535,9 +537,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(set * kTileN);
                 uint32_t va[32], vb[32];
-                if (!p.skip_epilogue) tmem_ld_32x32(taddr, va);
+                if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < (p.skip_epilogue ? 0 : kTileN / 32); c += 2) {
+                for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : kTileN / 32); c += 2) {
                     // make room: two chunks can add up to 64 entries to one list
                     unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
                     while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
@@ -624,7 +626,8 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 struct XresParams {
     int64_t n_rows;
     int     nq, k, C, kblocks, stages, tq;
-    int64_t nt;              // row tiles
+    int64_t nt;              // row tiles of this launch
+    int64_t tile0;           // first row tile of this launch
     int     groups;          // CTA pairs
     int     nq_pad;          // tq * 256
     uint64_t* lists;         // [groups][2 sets][nq_pad][C] raw candidate lists
@@ -683,7 +686,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 if (cta_rank == 0) mbar_expect_tx(x_full, x_bytes * CG);
                 for (int kb = 0; kb < p.kblocks; ++kb)
                     tma_load_2d<CG>(smem_x + kb * kQBlockBytes, &tmap_x, x_full, kb * kKBlock,
-                                    static_cast<int>(j * kTileN) + static_cast<int>(cta_rank) * kTileQ, p.row_policy);
+                                    static_cast<int>((p.tile0 + j) * kTileN) + static_cast<int>(cta_rank) * kTileQ, p.row_policy);
                 ++nload;
                 pending = false;
             };
@@ -694,7 +697,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                                      ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(kb * kKBlock),
-                                       "r"(static_cast<int>((j + 1) * kTileN) + static_cast<int>(cta_rank) * kTileQ)
+                                       "r"(static_cast<int>((p.tile0 + j + 1) * kTileN) + static_cast<int>(cta_rank) * kTileQ)
                                      : "memory");
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -769,6 +772,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             }
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
+            if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
             filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
         };
 
@@ -792,16 +796,16 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 const int64_t q2 = q_of(t2);
                 pf_n = n + 2; pf_cnt = p.counts[set_base + q2]; pf_tau = __ldcg(p.tau_g + q2);
             }
-            const int64_t row0 = j * kTileN;
+            const int64_t row0 = (p.tile0 + j) * kTileN;
             const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
             mbar_wait(tfull_bar(set), static_cast<uint32_t>((n >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(set * kTileN);
             uint32_t va[32], vb[32];
-            if (!p.skip_epilogue) tmem_ld_32x32(taddr, va);
+            if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < (p.skip_epilogue ? 0 : kTileN / 32); c += 2) {
+            for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : kTileN / 32); c += 2) {
                 unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
                 while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
                 tmem_wait_ld(va);
@@ -852,6 +856,17 @@ __global__ void queries_to_f16_kernel(const float* __restrict__ q, __half* __res
     }
 }
 
+
+// After the prefix phase: every query's shared threshold starts the bulk phase at the EXACT k-th
+// best score of the prefix rows (a valid lower bound of the final k-th best), in the kernel's
+// scaled score domain (keys hold unscaled-by-q_scale scores, i.e. already that domain).
+__global__ void seed_tau_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts,
+                                uint32_t* __restrict__ tau_g, int64_t nq, int k) {
+    const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (q >= nq) return;
+    if (counts[q] >= k) atomicMax(tau_g + q, f2ord(key_score(keys[q * k + k - 1])));
+}
+
 // ------------------------------------------------------------------ host side ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -898,55 +913,46 @@ bool mma_supported(const ivr_index* idx, int64_t nq, int k) {
     return idx->dpad <= kMaxKBlocks * kKBlock && k <= IVR_MAX_K;
 }
 
-template <int CG, int E>
-static int launch_mma(const CUtensorMap& tq, const CUtensorMap& tx, const MmaParams& p, int grid, size_t smem,
-                      cudaStream_t st) {
-    auto kern = search_mma_kernel<CG, E>;
-    IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kMmaThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    IVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tx, p));
-    return IVR_OK;
-}
+// ---- launch plans ---------------------------------------------------------------------
+// A plan describes one scoring launch over the row tiles [tile0, tile0 + nt): kernel parameters,
+// the scratch it needs, and how the merge kernel reads the candidate lists it leaves behind.
+struct Plan {
+    bool      xres = false;
+    int       cg = 2, grid = 0, E = 8;
+    size_t    smem = 0;
+    MmaParams q{};            // query-tile-resident
+    XresParams x{};           // row-tile-resident
+    size_t    list_bytes = 0, aux_bytes = 0;    // lists; state / counts / slot buffers
+    int       n_lists = 0;
+};
 
-static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
-                            int64_t id_offset, cudaStream_t st, int cg, bool first_batch) {
-    const int kcap = kcap_for(k);
-    const int C = 2 * kcap;
+static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t tile0, int64_t nt, Plan* pl) {
+    const int C = 2 * kcap_for(k);
     const int mq = kTileQ * cg;
-    MmaParams p{};
+    MmaParams& p = pl->q;
+    p = MmaParams{};
     p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.k = k; p.C = C;
     p.kblocks = idx->dpad / kKBlock;
     p.tq = static_cast<int>((nq + mq - 1) / mq);
-    p.nt = (idx->ntotal + kTileN - 1) / kTileN;
+    p.nt = nt; p.tile0 = tile0;
     p.nq_pad = p.tq * mq;
     int grid = idx->sm_count / cg * cg;
     p.groups = grid / cg;                                          // caller guarantees tq <= groups
-    // lockstep grid part + leftover part with equal work per group
     p.c = p.groups / p.tq;
     p.g_grid = p.c * p.tq;
     p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
-    if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;  // tail too small to split
+    if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;
     p.stagger = std::max(0, env_int("IVR_MMA_STAGGER", 1));
     p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
     {
         const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
     }
-    // smem: resident query tile + as many ring stages as fit
     const int stage_bytes = (kTileN / cg) * 128;
     const int q_bytes = p.kblocks * kQBlockBytes;
     p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - q_bytes) / stage_bytes);
     if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the row-tile ring", idx->dim); return IVR_EUNSUPPORTED; }
-    const size_t smem = 1024 + q_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
-    // segments per group and partial-result slots per query tile (mirrors the device schedule)
+    pl->smem = 1024 + q_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
     const int Gl = p.groups - p.g_grid;
     const int64_t ntl = p.nt - p.ntg, Ul = static_cast<int64_t>(p.tq) * ntl;
     int left_per_tile = 0;
@@ -961,93 +967,31 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
             if (ue > ub) p.segs_max = std::max(p.segs_max, static_cast<int>((ue - 1) / ntl - ub / ntl) + 1);
         }
     }
-    const int slots = 2 * (p.c + left_per_tile);
-
-    // workspace carve-up
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_q  = carve(static_cast<size_t>(p.nq_pad) * idx->dpad * 2);
-    const size_t o_sc = carve(static_cast<size_t>(p.nq_pad) * 4);
-    const size_t o_tg = carve(static_cast<size_t>(p.nq_pad) * 4);
-    const size_t o_l  = carve(static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * C * 8);
-    const size_t o_st = carve(static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * sizeof(int2));
-    const size_t o_k  = carve(static_cast<size_t>(slots) * p.nq_pad * k * 8);
-    const size_t o_c  = carve(static_cast<size_t>(slots) * p.nq_pad * 4);
-    const size_t tmp_keys = merge_tmp_entries(slots, nq, k);
-    const size_t o_t  = carve(tmp_keys * 8);
-    const size_t o_tc = carve((static_cast<size_t>(slots) * nq + 64) * 4);
-    IVR_TRY(ensure_ws(idx, off));
-    char* ws = static_cast<char*>(idx->ws);
-    __half* q_h = reinterpret_cast<__half*>(ws + o_q);
-    float* q_scale = reinterpret_cast<float*>(ws + o_sc);
-    p.tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
-    p.lists = reinterpret_cast<uint64_t*>(ws + o_l);
-    p.state = reinterpret_cast<int2*>(ws + o_st);
-    p.out_keys = reinterpret_cast<uint64_t*>(ws + o_k);
-    p.out_counts = reinterpret_cast<int*>(ws + o_c);
-    const bool timed = idx->timing && first_batch;
-
-    if (timed) cudaEventRecord(idx->ev[4], st);
-    {
-        const int64_t threads = static_cast<int64_t>(p.nq_pad) * 32;
-        queries_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-            q_dev, q_h, q_scale, p.tau_g, nq, p.nq_pad, idx->dim, idx->dpad);
-        IVR_CUDA(cudaGetLastError());
-        idx->launches[2]++;
-        IVR_CUDA(cudaMemsetAsync(p.out_counts, 0, static_cast<size_t>(slots) * p.nq_pad * 4, st));
-    }
-    if (timed) cudaEventRecord(idx->ev[5], st);
-
-    // TMA descriptors (the row descriptor is cached until the matrix moves or grows)
-    CUtensorMap tmq;
-    IVR_TRY(make_tmap(&tmq, q_h, p.nq_pad, idx->dpad, kTileQ));
-    if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != kTileN / cg) {
-        IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, kTileN / cg));
-        idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = kTileN / cg;
-    }
-    const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
-
-    if (timed) cudaEventRecord(idx->ev[0], st);
-    int rc;
-    if (cg == 2) rc = (kcap == 128) ? launch_mma<2, 8>(tmq, tmx, p, grid, smem, st) : launch_mma<2, 0>(tmq, tmx, p, grid, smem, st);
-    else         rc = (kcap == 128) ? launch_mma<1, 8>(tmq, tmx, p, grid, smem, st) : launch_mma<1, 0>(tmq, tmx, p, grid, smem, st);
-    IVR_TRY(rc);
-    idx->launches[0]++;
-    if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
-
-    MergeIn in{};
-    in.entries = p.out_keys; in.counts = p.out_counts;
-    in.list_stride = static_cast<int64_t>(p.nq_pad) * k; in.q_stride = k;
-    in.cnt_list_stride = p.nq_pad; in.cnt_q_stride = 1;
-    in.n_lists = slots; in.fixed_count = 0;
-    IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_t),
-                              reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1], q_scale));
-    if (timed) {
-        cudaEventRecord(idx->ev[3], st);
-        idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
-    }
+    pl->xres = false; pl->cg = cg; pl->grid = grid; pl->E = (C == 256) ? 8 : 0;
+    pl->n_lists = 2 * (p.c + left_per_tile);                       // output slots per query
+    pl->list_bytes = static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * C * 8;
+    pl->aux_bytes = static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * sizeof(int2) + 256 +
+                    static_cast<size_t>(pl->n_lists) * p.nq_pad * k * 8 + 256 +
+                    static_cast<size_t>(pl->n_lists) * p.nq_pad * 4 + 256;
     return IVR_OK;
 }
 
-
-// Row-tile-resident path: cta_group::2, any number of query tiles.
-static int search_mma_xres_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
-                                 int64_t id_offset, cudaStream_t st, bool first_batch) {
+static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int64_t nt, Plan* pl) {
     constexpr int cg = 2;
-    const int kcap = kcap_for(k);
-    const int C = 2 * kcap;
+    const int C = 2 * kcap_for(k);
     const int mq = kTileQ * cg;
-    XresParams p{};
+    XresParams& p = pl->x;
+    p = XresParams{};
     p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.k = k; p.C = C;
     p.kblocks = idx->dpad / kKBlock;
     p.tq = static_cast<int>((nq + mq - 1) / mq);
-    p.nt = (idx->ntotal + kTileN - 1) / kTileN;
+    p.nt = nt; p.tile0 = tile0;
     p.nq_pad = p.tq * mq;
     int grid = idx->sm_count / cg * cg;
     p.groups = grid / cg;
-    if (p.nt < p.groups) { p.groups = static_cast<int>(p.nt); grid = p.groups * cg; }
+    if (p.nt < p.groups) { p.groups = static_cast<int>(std::max<int64_t>(p.nt, 1)); grid = p.groups * cg; }
+    p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
     {
-        p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
         const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
     }
@@ -1055,75 +999,173 @@ static int search_mma_xres_batch(ivr_index* idx, const float* q_dev, int64_t nq,
     const int x_bytes = p.kblocks * kQBlockBytes;
     p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - x_bytes) / stage_bytes);
     if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the query ring", idx->dim); return IVR_EUNSUPPORTED; }
-    const size_t smem = 1024 + x_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
-    const int n_lists = p.groups * 2;
+    pl->smem = 1024 + x_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
+    pl->xres = true; pl->cg = cg; pl->grid = grid; pl->E = (C == 256) ? 8 : 0;
+    pl->n_lists = p.groups * 2;
+    pl->list_bytes = static_cast<size_t>(pl->n_lists) * p.nq_pad * C * 8;
+    pl->aux_bytes = static_cast<size_t>(pl->n_lists) * p.nq_pad * 4 + 256;
+    return IVR_OK;
+}
 
+template <typename Kern, typename Params>
+static int launch_cluster(Kern kern, const CUtensorMap& tq, const CUtensorMap& tx, const Params& p, int grid, int cg,
+                          size_t smem, cudaStream_t st) {
+    IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    IVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tx, p));
+    return IVR_OK;
+}
+
+// Runs one planned launch with its scratch at `lists` / `aux`; fills `in` for the merge kernel.
+static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, uint32_t* tau_g, char* lists, char* aux,
+                    int k, cudaStream_t st, MergeIn* in) {
+    *in = MergeIn{};
+    if (pl.xres) {
+        XresParams& p = pl.x;
+        p.tau_g = tau_g;
+        p.lists = reinterpret_cast<uint64_t*>(lists);
+        p.counts = reinterpret_cast<int*>(aux);
+        IVR_CUDA(cudaMemsetAsync(p.counts, 0, static_cast<size_t>(pl.n_lists) * p.nq_pad * 4, st));
+        IVR_TRY(pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                          : launch_cluster(search_mma_xres_kernel<0>, tmq, tmx, p, pl.grid, 2, pl.smem, st));
+        in->entries = p.lists; in->counts = p.counts;
+        in->list_stride = static_cast<int64_t>(p.nq_pad) * p.C; in->q_stride = p.C;
+        in->cnt_list_stride = p.nq_pad; in->cnt_q_stride = 1;
+        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 1;
+    } else {
+        MmaParams& p = pl.q;
+        p.tau_g = tau_g;
+        p.lists = reinterpret_cast<uint64_t*>(lists);
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return aux + o; };
+        p.state = reinterpret_cast<int2*>(carve(static_cast<size_t>(pl.grid) * p.segs_max * 2 * kTileQ * sizeof(int2)));
+        p.out_keys = reinterpret_cast<uint64_t*>(carve(static_cast<size_t>(pl.n_lists) * p.nq_pad * k * 8));
+        p.out_counts = reinterpret_cast<int*>(carve(static_cast<size_t>(pl.n_lists) * p.nq_pad * 4));
+        IVR_CUDA(cudaMemsetAsync(p.out_counts, 0, static_cast<size_t>(pl.n_lists) * p.nq_pad * 4, st));
+        int rc;
+        if (pl.cg == 2) rc = pl.E == 8 ? launch_cluster(search_mma_kernel<2, 8>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                       : launch_cluster(search_mma_kernel<2, 0>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        else            rc = pl.E == 8 ? launch_cluster(search_mma_kernel<1, 8>, tmq, tmx, p, pl.grid, 1, pl.smem, st)
+                                       : launch_cluster(search_mma_kernel<1, 0>, tmq, tmx, p, pl.grid, 1, pl.smem, st);
+        IVR_TRY(rc);
+        in->entries = p.out_keys; in->counts = p.out_counts;
+        in->list_stride = static_cast<int64_t>(p.nq_pad) * k; in->q_stride = k;
+        in->cnt_list_stride = p.nq_pad; in->cnt_q_stride = 1;
+        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 0;
+    }
+    return IVR_OK;
+}
+
+// One query batch.  Large shards are searched in TWO phases: a prefix of the rows first, whose exact
+// k-th best score per query then seeds the shared admission thresholds of the bulk phase -- the
+// fused top-k epilogue admits ~k/prefix_rows of the scores instead of re-learning its thresholds in
+// every CTA (measured: 22k-45k admissions per query without the seed vs ~2k with it).
+static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                            int64_t id_offset, cudaStream_t st, int cg, bool xres, bool first_batch) {
+    const int mq = kTileQ * (xres ? 2 : cg);
+    const int tq = static_cast<int>((nq + mq - 1) / mq);
+    const int64_t nq_pad = static_cast<int64_t>(tq) * mq;
+    const int64_t nt = (idx->ntotal + kTileN - 1) / kTileN;
+    // phase split (in row tiles): prefix = 1/16 of the rows, clamped to [256k, 2M] rows
+    int64_t ntA = 0;
+    if (env_int("IVR_MMA_TWO_PHASE", 1)) {
+        const int64_t lo = (256 << 10) / kTileN, hi = (2048 << 10) / kTileN;
+        ntA = std::min(std::max(nt / 16, lo), hi);
+        if (ntA * 4 > nt) ntA = 0;                                 // small shard: single phase
+    }
+    const int n_phases = ntA > 0 ? 2 : 1;
+    Plan plan[2];
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const int64_t t0 = (ph == 0) ? 0 : ntA;
+        const int64_t n = (n_phases == 1) ? nt : (ph == 0 ? ntA : nt - ntA);
+        IVR_TRY(xres ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
+    }
+    size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
+    for (int ph = 0; ph < n_phases; ++ph) {
+        list_bytes = std::max(list_bytes, plan[ph].list_bytes);
+        aux_bytes = std::max(aux_bytes, plan[ph].aux_bytes);
+        max_lists = std::max(max_lists, plan[ph].n_lists);
+    }
+    // workspace carve-up
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_q  = carve(static_cast<size_t>(p.nq_pad) * idx->dpad * 2);
-    const size_t o_sc = carve(static_cast<size_t>(p.nq_pad) * 4);
-    const size_t o_tg = carve(static_cast<size_t>(p.nq_pad) * 4);
-    const size_t o_l  = carve(static_cast<size_t>(n_lists) * p.nq_pad * C * 8);
-    const size_t o_c  = carve(static_cast<size_t>(n_lists) * p.nq_pad * 4);
-    const size_t tmp_keys = merge_tmp_entries(n_lists, nq, k);
+    const size_t o_q  = carve(static_cast<size_t>(nq_pad) * idx->dpad * 2);
+    const size_t o_sc = carve(static_cast<size_t>(nq_pad) * 4);
+    const size_t o_tg = carve(static_cast<size_t>(nq_pad) * 4);
+    const size_t o_l  = carve(list_bytes);
+    const size_t o_a  = carve(aux_bytes);
+    const size_t o_pk = carve(static_cast<size_t>(2) * nq * k * 8);      // per-phase merged keys [phase][nq][k]
+    const size_t o_pc = carve(static_cast<size_t>(2) * nq * 4);
+    const size_t tmp_keys = merge_tmp_entries(max_lists, nq, k);
     const size_t o_t  = carve(tmp_keys * 8);
-    const size_t o_tc = carve((static_cast<size_t>(n_lists) * nq + 64) * 4);
+    const size_t o_tc = carve((static_cast<size_t>(max_lists) * nq + 64) * 4);
     IVR_TRY(ensure_ws(idx, off));
     char* ws = static_cast<char*>(idx->ws);
     __half* q_h = reinterpret_cast<__half*>(ws + o_q);
     float* q_scale = reinterpret_cast<float*>(ws + o_sc);
-    p.tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
-    p.lists = reinterpret_cast<uint64_t*>(ws + o_l);
-    p.counts = reinterpret_cast<int*>(ws + o_c);
+    uint32_t* tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
+    uint64_t* ph_keys = reinterpret_cast<uint64_t*>(ws + o_pk);
+    int* ph_counts = reinterpret_cast<int*>(ws + o_pc);
+    uint64_t* tmp_e = reinterpret_cast<uint64_t*>(ws + o_t);
+    int* tmp_c = reinterpret_cast<int*>(ws + o_tc);
     const bool timed = idx->timing && first_batch;
 
     if (timed) cudaEventRecord(idx->ev[4], st);
     {
-        const int64_t threads = static_cast<int64_t>(p.nq_pad) * 32;
+        const int64_t threads = nq_pad * 32;
         queries_to_f16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-            q_dev, q_h, q_scale, p.tau_g, nq, p.nq_pad, idx->dim, idx->dpad);
+            q_dev, q_h, q_scale, tau_g, nq, nq_pad, idx->dim, idx->dpad);
         IVR_CUDA(cudaGetLastError());
         idx->launches[2]++;
-        IVR_CUDA(cudaMemsetAsync(p.counts, 0, static_cast<size_t>(n_lists) * p.nq_pad * 4, st));
     }
     if (timed) cudaEventRecord(idx->ev[5], st);
 
+    // TMA descriptors (the row descriptor is cached until the matrix moves or grows)
+    const int box_rows = kTileN / (xres ? 2 : cg);
     CUtensorMap tmq;
-    IVR_TRY(make_tmap(&tmq, q_h, p.nq_pad, idx->dpad, kTileQ));
-    if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != kTileN / cg) {
-        IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, kTileN / cg));
-        idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = kTileN / cg;
+    IVR_TRY(make_tmap(&tmq, q_h, nq_pad, idx->dpad, kTileQ));
+    if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != box_rows) {
+        IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, box_rows));
+        idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = box_rows;
     }
     const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
 
+    // scoring launches are bracketed together by ev[0]/ev[1]; the (tiny) per-phase merges run between
+    // them and are therefore included in "score_ms" when there are two phases
     if (timed) cudaEventRecord(idx->ev[0], st);
-    {
-        auto launch = [&](auto kern) -> int {
-            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(static_cast<unsigned>(grid));
-            cfg.blockDim = dim3(kMmaThreads);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            IVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmq, tmx, p));
-            return IVR_OK;
-        };
-        IVR_TRY(kcap == 128 ? launch(search_mma_xres_kernel<8>) : launch(search_mma_xres_kernel<0>));
+    for (int ph = 0; ph < n_phases; ++ph) {
+        MergeIn in;
+        IVR_TRY(run_plan(plan[ph], tmq, tmx, tau_g, ws + o_l, ws + o_a, k, st, &in));
+        idx->launches[0]++;
+        if (n_phases == 1) {
+            if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
+            IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, tmp_e, tmp_c, st, &idx->launches[1], q_scale));
+        } else {
+            IVR_TRY(merge_lists_keys(in, nq, k, ph_keys + static_cast<size_t>(ph) * nq * k,
+                                     ph_counts + static_cast<size_t>(ph) * nq, tmp_e, tmp_c, st, &idx->launches[1]));
+            if (ph == 0) {
+                seed_tau_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(ph_keys, ph_counts, tau_g, nq, k);
+                IVR_CUDA(cudaGetLastError());
+                idx->launches[1]++;
+            }
+        }
     }
-    idx->launches[0]++;
-    if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
-
-    MergeIn in{};
-    in.entries = p.lists; in.counts = p.counts;
-    in.list_stride = static_cast<int64_t>(p.nq_pad) * C; in.q_stride = C;
-    in.cnt_list_stride = p.nq_pad; in.cnt_q_stride = 1;
-    in.n_lists = n_lists; in.fixed_count = 0; in.raw = 1;
-    IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_t),
-                              reinterpret_cast<int*>(ws + o_tc), st, &idx->launches[1], q_scale));
+    if (n_phases == 2) {
+        if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
+        MergeIn in{};
+        in.entries = ph_keys; in.counts = ph_counts;
+        in.list_stride = nq * k; in.q_stride = k; in.cnt_list_stride = nq; in.cnt_q_stride = 1;
+        in.n_lists = 2; in.fixed_count = 0; in.raw = 0;
+        IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, tmp_e, tmp_c, st, &idx->launches[1], q_scale));
+    }
     if (timed) {
         cudaEventRecord(idx->ev[3], st);
         idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
@@ -1136,24 +1178,15 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // Mode selection: IVR_MMA_MODE = 0 auto, 1 query-tile-resident, 2 row-tile-resident.
     // Auto: the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up.
     const int mode = env_int("IVR_MMA_MODE", 0);
-    const int cg_env = cta_group_mode();
+    const int cg = cta_group_mode();
     const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2);
-    if (xres) {
-        const int64_t per_launch = 16384;                          // bounds the candidate-list workspace
-        for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
-            const int64_t b = std::min(per_launch, nq - q0);
-            IVR_TRY(search_mma_xres_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k,
-                                          id_offset, st, q0 == 0));
-        }
-        return IVR_OK;
-    }
-    // query-tile-resident: one launch handles at most (#groups) query tiles
-    const int cg = cg_env;
-    const int64_t per_launch = static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
+    // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
+    // one query tile per CTA group
+    const int64_t per_launch = xres ? 16384 : static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
     for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
         const int64_t b = std::min(per_launch, nq - q0);
         IVR_TRY(search_mma_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k, id_offset, st,
-                                 cg, q0 == 0));
+                                 cg, xres, q0 == 0));
     }
     return IVR_OK;
 }

@@ -186,6 +186,39 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
     return IVR_OK;
 }
 
+// Same reduction, but the result stays in key form: out_keys [nq, k] (descending, 0-padded) and
+// out_counts [nq].  Used between the two phases of the batched search.
+int merge_lists_keys(const MergeIn& in0, int64_t nq, int k, uint64_t* out_keys, int* out_counts,
+                     uint64_t* tmp_entries, int* tmp_counts, cudaStream_t st, int* n_launches) {
+    if (nq <= 0) return IVR_OK;
+    const int kpad = kpad_for(k);
+    const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
+    MergeIn in = in0;
+    uint64_t* ebuf = tmp_entries;
+    int*      cbuf = tmp_counts;
+    for (int level = 0; ; ++level) {
+        const bool last = in.n_lists <= kMergeFanIn;
+        const int groups = last ? 1 : (in.n_lists + kMergeFanIn - 1) / kMergeFanIn;
+        if (!last && (!ebuf || !cbuf)) { set_error("merge: scratch missing for %d lists", in.n_lists); return IVR_EINVAL; }
+        MergeOut out{};
+        out.entries = last ? out_keys : ebuf; out.counts = last ? out_counts : cbuf; out.nq = nq;
+        dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(groups));
+        merge_kernel<false><<<grid, kMergeThreads, smem, st>>>(in, out, last ? in.n_lists : kMergeFanIn, k, kpad);
+        IVR_CUDA(cudaGetLastError());
+        if (n_launches) ++*n_launches;
+        if (last) return IVR_OK;
+        MergeIn nx{};
+        nx.entries = ebuf; nx.counts = cbuf;
+        nx.list_stride = nq * k; nx.q_stride = k;
+        nx.cnt_list_stride = nq; nx.cnt_q_stride = 1;
+        nx.n_lists = groups; nx.fixed_count = 0; nx.raw = 0;
+        ebuf += static_cast<size_t>(groups) * nq * k;
+        cbuf += static_cast<size_t>(groups) * nq;
+        in = nx;
+        if (level > 4) { set_error("merge: too many levels"); return IVR_EINVAL; }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // (D, I) shard lists -> packed keys, for the post-all-gather merge
 // ---------------------------------------------------------------------------
