@@ -70,13 +70,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
         "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(cta) : "memory");
 }
+// try_wait with a suspend-time hint (same value CUTLASS uses): the thread is put to sleep by the
+// hardware until the phase completes instead of polling -- the producer / MMA-issuer / epilogue
+// warps share warp schedulers, and a polling waiter steals issue slots (and power) from the
+// warps that have work.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -1086,7 +1090,11 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     for (int ph = 0; ph < n_phases; ++ph) {
         const int64_t t0 = (ph == 0) ? 0 : ntA;
         const int64_t n = (n_phases == 1) ? nt : (ph == 0 ? ntA : nt - ntA);
-        IVR_TRY(xres ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
+        // the short prefix phase has to learn its thresholds from scratch: the query-tile-resident kernel
+        // (few, long candidate streams) does that better, so it is used for the prefix whenever the
+        // layouts agree (CTA pairs, one query tile per pair available)
+        const bool prefix_qres = xres && n_phases == 2 && ph == 0 && cg == 2 && tq <= idx->sm_count / 2;
+        IVR_TRY((xres && !prefix_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
     }
     size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
     for (int ph = 0; ph < n_phases; ++ph) {
@@ -1179,7 +1187,11 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // Auto: the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up.
     const int mode = env_int("IVR_MMA_MODE", 0);
     const int cg = cta_group_mode();
-    const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2);
+    // measured (4096 queries, k=100): 10 M rows 36 ms query-tile-resident vs 46 ms row-tile-resident;
+    // 100 M rows 416 ms vs 349 ms -- the row-tile-resident kernel pays a fixed warm-up but moves 9x
+    // fewer bytes, so it takes over for big shards
+    const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
+                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 32)) * 1000000);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
     const int64_t per_launch = xres ? 16384 : static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
