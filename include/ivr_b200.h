@@ -100,6 +100,8 @@ IVR_API int ivr_index_set_timing(ivr_index* idx, int enable);
 IVR_API int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]);
 /* which path the last search took (IVR_PATH_STREAM / IVR_PATH_MMA) */
 IVR_API int ivr_index_last_path(const ivr_index* idx);
+/* name of the dominant scoring kernel of the last search (static string, e.g. "search_mma_xres_kernel") */
+IVR_API const char* ivr_index_last_kernel(const ivr_index* idx);
 
 /* K5: merge per-shard top-k lists after the all-gather
  * (semantic precedent: system.py:1721-1746 concat + sort + truncate).

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "ivr_index_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ivr_index_last_timing": (C.c_int, [C.c_void_p, _c_f32p, _c_intp]),
     "ivr_index_last_path": (C.c_int, [C.c_void_p]),
+    "ivr_index_last_kernel": (C.c_char_p, [C.c_void_p]),
     "ivr_topk_merge_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ivr_normalize_l2": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int]),

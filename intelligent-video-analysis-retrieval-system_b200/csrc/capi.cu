@@ -251,6 +251,7 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
     }
     if (use != IVR_PATH_STREAM) { set_error("search: unknown path %d", path); return IVR_EINVAL; }
     idx->last_path = IVR_PATH_STREAM;
+    idx->last_kernel = "search_stream_kernel";
     return search_stream(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
 }
 
@@ -308,6 +309,7 @@ int ivr_index_last_timing(ivr_index* idx, float ms[3], int launches[3]) {
 }
 
 int ivr_index_last_path(const ivr_index* idx) { return idx ? idx->last_path : -1; }
+const char* ivr_index_last_kernel(const ivr_index* idx) { return idx ? idx->last_kernel : ""; }
 
 int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
                           int64_t nq, int k, float* D_out, int64_t* I_out, void* stream) {

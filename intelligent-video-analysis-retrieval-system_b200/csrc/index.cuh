@@ -40,6 +40,7 @@ struct ivr_index {
     bool        ev_valid[3] = {false, false, false};
     int         launches[3] = {0, 0, 0};
     int         last_path = 0;
+    const char* last_kernel = "";
 };
 
 namespace ivr {

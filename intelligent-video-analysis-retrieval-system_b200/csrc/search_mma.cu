@@ -1194,6 +1194,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
                                       idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 32)) * 1000000);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
+    idx->last_kernel = xres ? "search_mma_xres_kernel" : "search_mma_kernel";
     const int64_t per_launch = xres ? 16384 : static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
     for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
         const int64_t b = std::min(per_launch, nq - q0);

@@ -13,8 +13,6 @@ GPU through the C ABI (``_native``); there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
-import io
-import struct
 
 import numpy as np
 
@@ -26,7 +24,6 @@ __all__ = ["Index", "IndexFlatIP", "IndexFlatL2", "IndexIVFFlat", "normalize_L2"
 
 IO_FLAG_MMAP = 1
 METRIC_INNER_PRODUCT = 0
-_MAGIC = b"IVRB200\x01"
 
 
 def _as_f32_2d(x, d=None, what="x"):
@@ -39,7 +36,7 @@ def _as_f32_2d(x, d=None, what="x"):
 
 
 class IndexFlatIP:
-    """Exact inner-product index; rows live in HBM as bf16, ids are insertion order.
+    """Exact inner-product index; rows live in HBM as fp16, ids are insertion order.
 
     ``add`` / ``search`` / ``ntotal`` / ``d`` / ``is_trained`` / ``train`` / ``reset`` follow
     ``faiss.IndexFlatIP`` as used by the reference.
@@ -150,7 +147,8 @@ class IndexFlatIP:
         return {"score_ms": ms[0], "merge_ms": ms[1], "prep_ms": ms[2],
                 "score_launches": ln[0], "merge_launches": ln[1], "prep_launches": ln[2],
                 "path": {0: "empty", 1: "stream", 2: "mma"}.get(
-                    nat.lib.ivr_index_last_path(self._handle()), "?")}
+                    nat.lib.ivr_index_last_path(self._handle()), "?"),
+                "kernel": (nat.lib.ivr_index_last_kernel(self._handle()) or b"").decode()}
 
 
 Index = IndexFlatIP
