@@ -50,6 +50,8 @@ def parse_args():
     p.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     p.add_argument("--cpu-sample-queries", type=int, default=256)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true",
+                   help="skip the informational legs for BASELINE configs B (dedup) and C (single query)")
     return p.parse_args()
 
 
@@ -186,6 +188,91 @@ def measured_traffic(kernel, rows, dim, nq, k):
         if (e["kernel"], e["rows"], e["dim"], e["nq"], e["k"]) == (kernel, rows, dim, nq, k):
             return e["dram_bytes"]
     return None
+
+
+
+# ---------------------------------------------------------------------------- extras (N=1 only)
+def run_extras(dev, peaks):
+    """Informational legs (not the headline): BASELINE config C (10 M x 768, single query, the
+    streaming kernel vs the HBM roofline) and config B (dedup 1 M x 512, W=8, thr 0.95)."""
+    import ctypes as C
+    import torch
+    import ivr_b200
+    from ivr_b200 import _native as nat
+    out = {}
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    # ---- config C: single-query latency path ------------------------------------------
+    n, d = 10_000_000, 768
+    cen = centres(d, dev)
+    idx = ivr_b200.IndexFlatIP(d, device=dev.index)
+    idx.reserve(n)
+    for c in range(n // GEN_CHUNK):
+        idx.add(gen_rows(c, GEN_CHUNK, d, cen, dev, seed=79))
+    q = gen_queries(1, d, cen.cpu())
+    qd = q.to(dev)
+    idx.set_timing(True)
+    ks = []
+    for i in range(13):
+        idx.search_tensor(qd, 100)
+        t = idx.last_timing()
+        if i >= 3:
+            ks.append(t["score_ms"] + t["merge_ms"] + t["prep_ms"])
+            kern = t["score_ms"]
+    idx.set_timing(False)
+    qn = q.numpy()
+    for _ in range(3):
+        idx.search(qn, 100)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        idx.search(qn, 100)
+    lat = (time.perf_counter() - t0) / 20
+    gbs = n * d * 2 / (kern * 1e-3) / 1e9
+    out["config_c_single_query_10Mx768"] = {
+        "kernel": "search_stream_kernel", "kernel_ms": kern, "device_ms_per_query": statistics.median(ks),
+        "e2e_latency_ms_host_buffers": lat * 1e3, "queries_per_s_e2e": 1.0 / lat,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                     "algorithmic_bytes_per_launch": n * d * 2}}
+    idx.close()
+    del idx
+    torch.cuda.empty_cache()
+    # ---- config B: near-duplicate pruning ----------------------------------------------
+    n, d, w = 1_000_000, 512, 8
+    g = torch.Generator(device=dev).manual_seed(7)
+    lens = torch.distributions.Geometric(probs=torch.tensor(1.0 / 20)).sample((n // 10,)).to(torch.int64) + 1
+    sid = torch.repeat_interleave(torch.arange(lens.numel()), lens)[:n].to(dev)
+    base = torch.randn(int(sid.max().item()) + 1, d, generator=g, device=dev)
+    sig = 0.10 + 0.25 * torch.rand(n, 1, generator=g, device=dev)
+    x = ((base[sid] + sig * torch.randn(n, d, generator=g, device=dev)) * 3.0).contiguous()
+    cos = torch.empty(n, dtype=torch.float32, device=dev)
+    mask = torch.empty(n, dtype=torch.int32, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    nat.check(nat.lib.ivr_consecutive_cosine_device(dev.index, x.data_ptr(), n, d, cos.data_ptr(), st))
+    torch.cuda.synchronize()
+    cuts = torch.nonzero(cos[1:] < 0.75).flatten() + 1
+    starts = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cuts])
+    ends = torch.cat([cuts, torch.tensor([n], device=dev)]) - 1
+    ok = (ends - starts + 1) >= 2
+    a, b = starts[ok].contiguous(), ends[ok].contiguous()
+    nat.check(nat.lib.ivr_dedup_set_timing(1))
+    ms = (C.c_float * 2)()
+    best = None
+    for _ in range(8):
+        nat.check(nat.lib.ivr_dedup_window_device(dev.index, x.data_ptr(), n, d, a.data_ptr(), b.data_ptr(),
+                                                  a.numel(), w, C.c_float(0.95), keep.data_ptr(), cos.data_ptr(),
+                                                  mask.data_ptr(), st))
+        torch.cuda.synchronize()
+        nat.check(nat.lib.ivr_dedup_last_timing(ms))
+        if best is None or ms[0] + ms[1] < best[0] + best[1]:
+            best = (ms[0], ms[1])
+    nat.check(nat.lib.ivr_dedup_set_timing(0))
+    gbs = n * d * 4 / (best[0] * 1e-3) / 1e9
+    out["config_b_dedup_1Mx512_w8"] = {
+        "kernel": "banded_cosine_rw_kernel", "kernel_ms": best[0], "resolve_ms": best[1],
+        "frames_per_s": n / ((best[0] + best[1]) * 1e-3), "kept": int(keep.sum().item()), "scenes": int(a.numel()),
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                     "algorithmic_bytes_per_launch": n * d * 4}}
+    return out
 
 
 # ---------------------------------------------------------------------------- our arm
@@ -407,6 +494,11 @@ def run_ours(args):
                                             "recall_vs_exact_fp32": recall, "tol": 1e-3}}
         if cpu:
             out["cpu_baseline"] = cpu
+        if world == 1 and not args.no_extras:
+            try:
+                out["extras"] = run_extras(dev, peaks)
+            except Exception as e:                                   # informational legs never sink the headline
+                out["extras"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1191,7 +1191,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // 100 M rows 416 ms vs 349 ms -- the row-tile-resident kernel pays a fixed warm-up but moves 9x
     // fewer bytes, so it takes over for big shards
     const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
-                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 32)) * 1000000);
+                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 16)) * 1000000);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
     idx->last_kernel = xres ? "search_mma_xres_kernel" : "search_mma_kernel";

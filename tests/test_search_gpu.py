@@ -119,6 +119,20 @@ def test_mma_more_query_tiles_than_cta_groups(cta_group):
     check(idx, ref, xq, 10, path=2)
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["query_tile_resident", "row_tile_resident"])
+def test_mma_two_phase_large_shard(mode, monkeypatch):
+    """A shard big enough (>= 4 x 256k rows) for the two-phase search: the prefix phase seeds the
+    admission thresholds of the bulk phase; results must stay exact."""
+    monkeypatch.setenv("IVR_MMA_MODE", str(mode))
+    xb = synth.clip_like(1_200_000, 64, seed=73, n_centres=512)
+    xq = synth.clip_like(300, 64, seed=74, n_centres=512)
+    idx, ref = build(xb)
+    D2, I2 = check(idx, ref, xq, 100, path=2)
+    monkeypatch.setenv("IVR_MMA_TWO_PHASE", "0")                 # single phase must give the same ids/scores
+    D1, I1 = check(idx, ref, xq, 100, path=2)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+
+
 def test_mma_and_stream_paths_agree():
     xb = synth.clip_like(50_000, 512, seed=67, n_centres=128)
     xq = synth.clip_like(8, 512, seed=68, n_centres=128)
