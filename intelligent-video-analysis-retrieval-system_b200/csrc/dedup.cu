@@ -266,7 +266,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int DV>
-__global__ void __launch_bounds__(kRwWarps * 32, 2)
+__global__ void __launch_bounds__(kRwWarps * 32, 3)
 banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
                         uint32_t* __restrict__ masks, float* __restrict__ cos_prev) {
     extern __shared__ float4 s_stage[];         // [kRwWarps][kRwSlots][DV * 32]
@@ -458,7 +458,7 @@ int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, u
     const int variant = env_flag("IVR_DEDUP_KERNEL", 0);
     if (aligned && window <= kRwWindow && (d == 512 || d == 384) && variant == 0) {
         const size_t smem = static_cast<size_t>(kRwWarps) * kRwSlots * d * sizeof(float);
-        int64_t grid = static_cast<int64_t>(sm_count) * 2;                  // persistent: 2 CTAs per SM
+        int64_t grid = static_cast<int64_t>(sm_count) * 3;                  // persistent: 3 CTAs per SM
         const int64_t max_grid = (n + 255) / 256;
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
