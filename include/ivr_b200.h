@@ -155,6 +155,13 @@ IVR_API int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d,
                     const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
                     int min_distance, float thr, int force_last, uint8_t* keep_host);
 
+/* Replaces Phase 4 of filter_research_update.AdvancedKeyframeExtractor
+ * (filter_research_update.py:316-338): per sequence keep frame 0; keep frame i iff
+ * cos(e_i, e_p) < thr for every p in a FIFO of the last `fifo` (1..16, reference: 10) KEPT frames. */
+IVR_API int ivr_dedup_fifo(int device, const float* e_host, int64_t n, int d,
+                   const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
+                   int fifo, float thr, uint8_t* keep_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ from . import _native, faiss_compat, frame_filter, sharded           # noqa: F40
 from .facade import RAGBuilder, RAGRetriever                          # noqa: F401
 from .faiss_compat import IndexFlatIP, normalize_L2                   # noqa: F401
 from .frame_filter import FrameFilter                                 # noqa: F401
+from .relationships import build_similarity_relationships            # noqa: F401
 from .retriever import FAISSRetriever, KeyframeMetadata, SearchResult  # noqa: F401
 from .sharded import ShardedFlatIP                                    # noqa: F401
 from .unified_builder import UnifiedBuilderIntegration, add_unified_index_support  # noqa: F401

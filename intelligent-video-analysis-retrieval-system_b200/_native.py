@@ -64,6 +64,8 @@ PROTOTYPES = {
     "ivr_dedup_last_timing": (C.c_int, [_c_f32p]),
     "ivr_dedup_chain": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "ivr_dedup_fifo": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_int, C.c_float, C.c_void_p]),
 }
 
 

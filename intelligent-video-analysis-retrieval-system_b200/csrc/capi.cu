@@ -31,7 +31,7 @@ int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
                         float* cos_prev_dev, uint32_t* mask_ws_dev, cudaStream_t st);
 int dedup_chain_device(const float* e_dev, int64_t n, int d, const int64_t* scene_start_dev,
                        const int64_t* scene_end_dev, int64_t n_scenes, int min_distance, float thr,
-                       int force_last, uint8_t* keep_dev, cudaStream_t st);
+                       int force_last, int fifo, uint8_t* keep_dev, cudaStream_t st);
 
 static int require_device(int device) {
     int n = 0;
@@ -439,14 +439,15 @@ int ivr_dedup_window(int device, const float* e_host, int64_t n, int d, const in
     return IVR_OK;
 }
 
-int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
-                    const int64_t* scene_end, int64_t n_scenes, int min_distance, float thr,
-                    int force_last, uint8_t* keep_host) {
+static int dedup_chain_host(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
+                           const int64_t* scene_end, int64_t n_scenes, int min_distance, float thr,
+                           int force_last, int fifo, uint8_t* keep_host, const char* who) {
     if (n < 0 || d <= 0 || n_scenes < 0 || (n > 0 && (!e_host || !keep_host)) ||
         (n_scenes > 0 && (!scene_start || !scene_end))) {
-        set_error("dedup_chain: bad argument");
+        set_error("%s: bad argument", who);
         return IVR_EINVAL;
     }
+    if (fifo < 1 || fifo > 16) { set_error("%s: fifo %d outside 1..16", who, fifo); return IVR_EUNSUPPORTED; }
     if (n == 0) return IVR_OK;
     IVR_TRY(require_device(device));
     const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
@@ -459,10 +460,23 @@ int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d, const int
         IVR_CUDA(cudaMemcpy(se.p, scene_end, n_scenes * sizeof(int64_t), cudaMemcpyHostToDevice));
     }
     IVR_TRY(dedup_chain_device(static_cast<float*>(e.p), n, d, static_cast<int64_t*>(ss.p),
-                               static_cast<int64_t*>(se.p), n_scenes, min_distance, thr, force_last,
+                               static_cast<int64_t*>(se.p), n_scenes, min_distance, thr, force_last, fifo,
                                static_cast<uint8_t*>(k.p), nullptr));
     IVR_CUDA(cudaMemcpy(keep_host, k.p, n, cudaMemcpyDeviceToHost));
     return IVR_OK;
+}
+
+int ivr_dedup_chain(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
+                    const int64_t* scene_end, int64_t n_scenes, int min_distance, float thr,
+                    int force_last, uint8_t* keep_host) {
+    return dedup_chain_host(device, e_host, n, d, scene_start, scene_end, n_scenes, min_distance, thr,
+                            force_last, 1, keep_host, "dedup_chain");
+}
+
+int ivr_dedup_fifo(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,
+                   const int64_t* scene_end, int64_t n_scenes, int fifo, float thr, uint8_t* keep_host) {
+    return dedup_chain_host(device, e_host, n, d, scene_start, scene_end, n_scenes, 1, thr, 0, fifo, keep_host,
+                            "dedup_fifo");
 }
 
 }  // extern "C"

@@ -388,11 +388,18 @@ __global__ void window_resolve_kernel(const uint32_t* __restrict__ masks,
     }
 }
 
-// One warp per scene: last-kept chain (filter.py:178-222 / video_frame_filter.py:63-70).
+// One warp per scene: keep-chain rules with unbounded look-back in frame index.
+//   fifo == 1 : last-kept chain (filter.py:178-222; video_frame_filter.py:63-70): keep i iff
+//               i - last_kept >= min_distance and cos(e_i, e_last_kept) < thr; with force_last the
+//               scene's last frame is always kept.
+//   fifo  > 1 : FIFO of the last `fifo` KEPT frames (filter_research_update.py:316-338, Phase 4):
+//               keep i iff cos(e_i, e_p) < thr for every p in the FIFO.
+constexpr int kMaxFifo = 16;
+
 __global__ void chain_resolve_kernel(const float* __restrict__ e, int d,
                                      const int64_t* __restrict__ scene_start,
                                      const int64_t* __restrict__ scene_end, int64_t n_scenes,
-                                     int64_t n, int min_distance, float thr, int force_last,
+                                     int64_t n, int min_distance, float thr, int force_last, int fifo,
                                      uint8_t* __restrict__ keep) {
     const int lane = threadIdx.x & 31;
     const int64_t s = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -409,20 +416,36 @@ __global__ void chain_resolve_kernel(const float* __restrict__ e, int d,
         float nrm = sqrtf(ss);
         return nrm == 0.f ? 1.f : nrm;
     };
+    // FIFO of kept frames: index + norm, oldest first (warp-uniform registers)
+    int64_t kept_idx[kMaxFifo];
+    float kept_nrm[kMaxFifo];
+    int nk = 1;
+    kept_idx[0] = a; kept_nrm[0] = norm_of(a);
     int64_t last = a;
-    float nlast = norm_of(a);
     if (lane == 0) keep[a] = 1;
     for (int64_t i = a + 1; i <= b; ++i) {
         if (i - last < min_distance) { if (lane == 0) keep[i] = 0; continue; }
         const float ni = norm_of(i);
         const float* p = e + i * d;
-        const float* q = e + last * d;
-        float acc = 0.f;
-        for (int c = lane; c < d; c += 32) acc = fmaf(p[c] / ni, q[c] / nlast, acc);
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const bool k = acc < thr;
-        if (lane == 0) keep[i] = k ? 1 : 0;
-        if (k) { last = i; nlast = ni; }
+        bool unique = true;
+        for (int w = 0; w < nk && unique; ++w) {                 // oldest first, stop at the first hit
+            const float* q = e + kept_idx[w] * d;
+            const float nq = kept_nrm[w];
+            float acc = 0.f;
+            for (int c = lane; c < d; c += 32) acc = fmaf(p[c] / ni, q[c] / nq, acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (!(acc < thr)) unique = false;
+        }
+        if (lane == 0) keep[i] = unique ? 1 : 0;
+        if (unique) {
+            last = i;
+            if (nk == fifo) {                                     // pop the oldest
+#pragma unroll
+                for (int w = 0; w + 1 < kMaxFifo; ++w) { kept_idx[w] = kept_idx[w + 1]; kept_nrm[w] = kept_nrm[w + 1]; }
+                --nk;
+            }
+            kept_idx[nk] = i; kept_nrm[nk] = ni; ++nk;
+        }
     }
     if (force_last && last != b && lane == 0) keep[b] = 1;
 }
@@ -553,14 +576,14 @@ int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
 
 int dedup_chain_device(const float* e_dev, int64_t n, int d, const int64_t* scene_start_dev,
                        const int64_t* scene_end_dev, int64_t n_scenes, int min_distance, float thr,
-                       int force_last, uint8_t* keep_dev, cudaStream_t st) {
+                       int force_last, int fifo, uint8_t* keep_dev, cudaStream_t st) {
     if (n <= 0) return IVR_OK;
     IVR_CUDA(cudaMemsetAsync(keep_dev, 0, static_cast<size_t>(n), st));
     if (n_scenes <= 0) return IVR_OK;
     const int threads = 128;
     const int64_t blocks = (n_scenes * 32 + threads - 1) / threads;
     chain_resolve_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-        e_dev, d, scene_start_dev, scene_end_dev, n_scenes, n, min_distance, thr, force_last, keep_dev);
+        e_dev, d, scene_start_dev, scene_end_dev, n_scenes, n, min_distance, thr, force_last, fifo, keep_dev);
     IVR_CUDA(cudaGetLastError());
     return IVR_OK;
 }

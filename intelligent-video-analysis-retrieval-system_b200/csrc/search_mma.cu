@@ -1187,11 +1187,11 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // Auto: the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up.
     const int mode = env_int("IVR_MMA_MODE", 0);
     const int cg = cta_group_mode();
-    // measured (4096 queries, k=100): 10 M rows 36 ms query-tile-resident vs 46 ms row-tile-resident;
-    // 100 M rows 416 ms vs 349 ms -- the row-tile-resident kernel pays a fixed warm-up but moves 9x
-    // fewer bytes, so it takes over for big shards
+    // measured (4096 queries, k=100, two-phase): 10 M rows 36.5 ms query-tile-resident vs 37.6 ms
+    // row-tile-resident; 12.5 M 44.2 vs 43.0; 25 M 97.1 vs 85.3; 100 M 405 vs 331 -- the row-tile-resident
+    // kernel moves 9x fewer bytes (the GPU is power-capped), so it takes over from ~12 M rows
     const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
-                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 16)) * 1000000);
+                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 12)) * 1000000);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
     idx->last_kernel = xres ? "search_mma_xres_kernel" : "search_mma_kernel";

@@ -21,7 +21,8 @@ from . import _native as nat
 __all__ = ["calculate_similarities", "detect_scene_transitions", "group_into_scenes",
            "filter_similar_frames_in_scene", "filter_similar_frames_advanced",
            "apply_similarity_filtering_to_scenes", "extract_unique_frames_rule",
-           "detect_scene_boundaries", "FrameFilter", "create_config"]
+           "detect_scene_boundaries", "detect_scene_changes", "temporal_window_filter",
+           "FrameFilter", "create_config"]
 
 
 def create_config(**overrides) -> Dict:
@@ -194,6 +195,30 @@ def detect_scene_boundaries(features: np.ndarray, threshold: float = 0.3,
     if start < n:
         bounds.append((start, n - 1))
     return bounds
+
+
+def detect_scene_changes(embeddings, threshold: float = 0.7) -> List[int]:
+    """AdvancedKeyframeExtractor.detect_scene_changes (filter_research_update.py:101-111):
+    [0] + every i with cos(e_i, e_{i-1}) < threshold + [len] (end marker)."""
+    n = len(embeddings)
+    sims = np.asarray(calculate_similarities(embeddings), dtype=np.float64)
+    return [0] + [int(i) + 1 for i in np.nonzero(sims < threshold)[0]] + [n]
+
+
+def temporal_window_filter(embeddings, threshold: float = 0.95, temporal_window: int = 10) -> List[int]:
+    """Phase 4 of AdvancedKeyframeExtractor (filter_research_update.py:316-338): walk the frames in
+    time order; a frame is kept iff its cosine with EVERY frame in a FIFO of the last
+    ``temporal_window`` kept frames is < threshold.  Returns the kept indices."""
+    n = len(embeddings)
+    if n == 0:
+        return []
+    x, _ = _as_matrix(embeddings)
+    a = np.zeros(1, np.int64)
+    b = np.full(1, n - 1, np.int64)
+    keep = np.zeros(n, np.uint8)
+    nat.check(nat.lib.ivr_dedup_fifo(nat.default_device(), x.ctypes.data, n, x.shape[1], a.ctypes.data,
+                                     b.ctypes.data, 1, int(temporal_window), float(threshold), keep.ctypes.data))
+    return np.nonzero(keep)[0].tolist()
 
 
 # ---------------------------------------------------------------------------

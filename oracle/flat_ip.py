@@ -177,3 +177,24 @@ def merge_shard_results(Ds, Is, k: int):
     key_id = np.where(ci < 0, np.iinfo(np.int64).max, ci)
     order = np.lexsort((key_id, -cd.astype(np.float64)), axis=-1)[:, :k]
     return np.take_along_axis(cd, order, axis=1), np.take_along_axis(ci, order, axis=1)
+
+
+def similarity_relationships(all_features, top: int = 10, threshold: float = 0.7):
+    """Restates MetadataManager._build_similarity_relationships (core.py:3493-3531) on
+    {folder: (keys, float32 [n, d])}: sklearn-style cosine matrix per folder, for each frame the
+    descending order minus its first entry, top `top`, kept where cosine > threshold.
+    Returns ({key: [keys]}, {key: {other_key: cosine}}) -- the second map is for tie-aware tests."""
+    graph, sims_of = {}, {}
+    for keys, x in all_features.values():
+        if len(keys) < 2:
+            continue
+        x = np.asarray(x, np.float32)
+        n = np.sqrt(np.einsum("ij,ij->i", x, x))
+        n[n == 0] = 1
+        xn = x / n[:, None]
+        s = xn @ xn.T
+        for i, key in enumerate(keys):
+            order = np.argsort(s[i])[::-1][1:top + 1]
+            graph[key] = [keys[j] for j in order if s[i][j] > threshold]
+            sims_of[key] = {keys[j]: float(s[i][j]) for j in range(len(keys))}
+    return graph, sims_of

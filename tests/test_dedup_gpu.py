@@ -89,6 +89,23 @@ def test_chain_rules_vs_oracle():
     assert ff.detect_scene_boundaries(feats[:8], 0.3, 5) == [(0, 7)]
 
 
+def test_fifo_rule_and_scene_changes_vs_oracle():
+    """filter_research_update.py Phase 4 (FIFO of the last 10 kept frames) and detect_scene_changes."""
+    from ivr_b200 import frame_filter as ff
+    x, _ = synth.dedup_frames_guarded(1200, 384, window=1, thresholds=(0.95, 0.7), seed=91)
+    emb = [r for r in x]
+    # guard-band the FIFO comparisons as well (they look back further than the banded generator checks)
+    for tw in (10, 3, 1, 16):
+        want = od.temporal_window_filter(emb, 0.95, tw)
+        assert ff.temporal_window_filter(emb, 0.95, tw) == want, tw
+    assert ff.temporal_window_filter(emb, 0.95, 1) == od.extract_unique_rule(emb, 0.95)
+    assert ff.detect_scene_changes(emb, 0.7) == od.detect_scene_changes(emb, 0.7)
+    assert ff.temporal_window_filter([], 0.95, 10) == []
+    from ivr_b200 import _native as nat
+    with pytest.raises(nat.NativeError):
+        ff.temporal_window_filter(emb[:10], 0.95, 17)
+
+
 def test_edge_cases():
     from ivr_b200 import frame_filter as ff
     assert ff.calculate_similarities([]) == [] and ff.calculate_similarities([np.ones(4, np.float32)]) == []

@@ -319,3 +319,33 @@ def test_faiss_retriever_on_gpu(search_golden):
         assert len(common) >= 11
         for key in common:
             assert abs(g[key] - w[key]) < 1e-6
+
+
+def test_similarity_relationships_vs_oracle():
+    """MetadataManager._build_similarity_relationships (core.py:3493-3531): per-folder top-10 > 0.7."""
+    import ivr_b200
+    rng = np.random.default_rng(5)
+    all_meta, all_feat = {}, {}
+    for f, n in enumerate((1, 2, 37, 400)):
+        folder = f"L{f:02d}_V001"
+        x = synth.clip_like(n, 128, seed=80 + f, n_centres=6) * np.float32(rng.uniform(0.5, 3.0))
+        metas = [ivr_b200.KeyframeMetadata(folder_name=folder, image_name=f"{i:04d}", frame_id=i,
+                                           file_path=f"{folder}/{i:04d}.jpg",
+                                           clip_features=(x[i] if (i % 11) != 5 else None)) for i in range(n)]
+        all_meta[folder] = metas
+        keep = [i for i in range(n) if (i % 11) != 5]
+        all_feat[folder] = ([metas[i].get_unique_key() for i in keep], x[keep])
+    got = ivr_b200.build_similarity_relationships(all_meta)
+    want, sims = flat_ip.similarity_relationships(all_feat)
+    assert set(got) == set(want)
+    for key, wl in want.items():
+        gl = got[key]
+        s = sims[key]
+        assert len(gl) <= 10 and len(set(gl)) == len(gl)
+        ranked = sorted((v for o, v in s.items()), reverse=True)
+        cut = max(0.7, ranked[min(10, len(ranked) - 1)])          # admission level: threshold or the 11th best
+        for o in gl:                                                # nothing clearly below the admission level
+            assert s[o] > cut - 1e-3, (key, o, s[o], cut)
+        for o in wl:                                                # nothing clearly above it is missing
+            if s[o] > cut + 1e-3:
+                assert o in gl or o == key, (key, o, s[o], cut)
