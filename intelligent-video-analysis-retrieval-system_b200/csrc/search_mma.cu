@@ -254,7 +254,7 @@ __device__ __forceinline__ float warp_compact_raw(uint64_t* list, int cnt, int k
 // chains); a warp vote per group skips groups without survivors, so the common "one survivor in
 // the whole warp-chunk" case costs 8 predicated stores instead of 32.
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float tau, int& cnt, uint64_t* my_list,
-                                             uint32_t rowc, int col0, int nvalid) {
+                                             uint32_t rowc, int col0, int nvalid, int tile_rows = kTileN) {
     float g8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -264,7 +264,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float tau,
     }
     const float m = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3]));
     if (!__any_sync(0xffffffffu, m > tau)) return;
-    if (nvalid == kTileN) {
+    if (nvalid == tile_rows) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (!__any_sync(0xffffffffu, g8[g] > tau)) continue;       // warp-uniform
@@ -632,6 +632,7 @@ struct XresParams {
     int     nq, k, C, kblocks, stages, tq;
     int64_t nt;              // row tiles of this launch
     int64_t tile0;           // first row tile of this launch
+    int     tn;              // rows per tile (256 or 128)
     int     groups;          // CTA pairs
     int     nq_pad;          // tq * 256
     uint64_t* lists;         // [groups][2 sets][nq_pad][C] raw candidate lists
@@ -641,7 +642,8 @@ struct XresParams {
     int       skip_epilogue;   // debug/perf probe: drain nothing (results are garbage)
 };
 
-template <int E>
+// TN = rows per tile: 256 for dpad <= 512, 128 for dpad <= 1024 (the resident tile stays <= 128 KB per CTA).
+template <int E, int TN>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                        const XresParams p) {
@@ -653,7 +655,8 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int group = blockIdx.x / CG;
 
     constexpr uint32_t stage_bytes = kTileQ * 128;               // one query k-block per CTA: 16 KB
-    const uint32_t x_bytes = p.kblocks * kQBlockBytes;           // this CTA's half of the row tile
+    constexpr uint32_t x_block = (TN / CG) * 128;                 // one k-block of this CTA's half of the row tile
+    const uint32_t x_bytes = p.kblocks * x_block;
     const uint32_t smem_x = smem_base;
     const uint32_t smem_s = smem_x + x_bytes;
     const uint32_t bars = smem_s + p.stages * stage_bytes;
@@ -689,8 +692,8 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 if (nload > 0) mbar_wait(x_empty, (nload - 1) & 1);  // MMAs finished with the old row tile
                 if (cta_rank == 0) mbar_expect_tx(x_full, x_bytes * CG);
                 for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d<CG>(smem_x + kb * kQBlockBytes, &tmap_x, x_full, kb * kKBlock,
-                                    static_cast<int>((p.tile0 + j) * kTileN) + static_cast<int>(cta_rank) * kTileQ, p.row_policy);
+                    tma_load_2d<CG>(smem_x + kb * x_block, &tmap_x, x_full, kb * kKBlock,
+                                    static_cast<int>((p.tile0 + j) * TN) + static_cast<int>(cta_rank) * (TN / CG), p.row_policy);
                 ++nload;
                 pending = false;
             };
@@ -701,7 +704,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                                      ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(kb * kKBlock),
-                                       "r"(static_cast<int>((p.tile0 + j + 1) * kTileN) + static_cast<int>(cta_rank) * kTileQ)
+                                       "r"(static_cast<int>((p.tile0 + j + 1) * TN) + static_cast<int>(cta_rank) * (TN / CG))
                                      : "memory");
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -721,7 +724,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         if (nload > 0) mbar_wait(x_empty, (nload - 1) & 1);
     } else if (warp == 1 && lane == 0) {
         // ============================ MMA issuer (leader CTA) =================
-        constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
+        constexpr uint32_t idesc = make_idesc(kTileQ * CG, TN);
         int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0; int64_t n = 0;
         for (int64_t j = j0; j < j1; ++j) {
             if (cta_rank == 0) mbar_wait(x_full, nload & 1);
@@ -732,12 +735,12 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     const uint32_t acc_phase = static_cast<uint32_t>((n >> 1) & 1);
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * TN);
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t a0 = smem_s + stage * stage_bytes;       // A: streamed query k-block
-                        const uint32_t b0 = smem_x + kb * kQBlockBytes;         // B: resident row-tile k-block
+                        const uint32_t b0 = smem_x + kb * x_block;               // B: resident row-tile k-block
 #pragma unroll
                         for (int k4 = 0; k4 < kKBlock / 16; ++k4)
                             umma_f16<CG>(tmem_d, make_smem_desc(a0 + k4 * 32), make_smem_desc(b0 + k4 * 32), idesc,
@@ -777,7 +780,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
             if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
-            filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
+            filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid, TN);
         };
 
         const int64_t n_units = (j1 - j0) * p.tq;
@@ -800,23 +803,23 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 const int64_t q2 = q_of(t2);
                 pf_n = n + 2; pf_cnt = p.counts[set_base + q2]; pf_tau = __ldcg(p.tau_g + q2);
             }
-            const int64_t row0 = (p.tile0 + j) * kTileN;
-            const int nvalid = static_cast<int>(min(static_cast<int64_t>(kTileN), p.n_rows - row0));
+            const int64_t row0 = (p.tile0 + j) * TN;
+            const int nvalid = static_cast<int>(min(static_cast<int64_t>(TN), p.n_rows - row0));
             mbar_wait(tfull_bar(set), static_cast<uint32_t>((n >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(set * kTileN);
+                                   static_cast<uint32_t>(set * TN);
             uint32_t va[32], vb[32];
             if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : kTileN / 32); c += 2) {
+            for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : TN / 32); c += 2) {
                 unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
                 while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
                 tmem_wait_ld(va);
                 tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                 process_chunk(va, c, row0, nvalid);
                 tmem_wait_ld(vb);
-                if (c + 2 < kTileN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                if (c + 2 < TN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
                 process_chunk(vb, c + 1, row0, nvalid);
             }
             p.counts[idx] = cnt;
@@ -914,7 +917,7 @@ static int cta_group_mode() { return env_int("IVR_MMA_CTA_GROUP", 2) == 1 ? 1 : 
 
 bool mma_supported(const ivr_index* idx, int64_t nq, int k) {
     (void)nq;
-    return idx->dpad <= kMaxKBlocks * kKBlock && k <= IVR_MAX_K;
+    return idx->dpad <= 2 * kMaxKBlocks * kKBlock && k <= IVR_MAX_K;     // up to 1024 dims
 }
 
 // ---- launch plans ---------------------------------------------------------------------
@@ -980,6 +983,8 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
     return IVR_OK;
 }
 
+static int xres_tile_rows(const ivr_index* idx) { return idx->dpad <= 512 ? 256 : 128; }
+
 static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int64_t nt, Plan* pl) {
     constexpr int cg = 2;
     const int C = 2 * kcap_for(k);
@@ -999,8 +1004,9 @@ static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int
         const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
     }
+    p.tn = xres_tile_rows(idx);
     const int stage_bytes = kTileQ * 128;
-    const int x_bytes = p.kblocks * kQBlockBytes;
+    const int x_bytes = p.kblocks * (p.tn / cg) * 128;
     p.stages = std::min(12, (kSmemBudget - 1024 - kBarrierBytes - x_bytes) / stage_bytes);
     if (p.stages < 2) { set_error("search_mma: dim %d leaves no room for the query ring", idx->dim); return IVR_EUNSUPPORTED; }
     pl->smem = 1024 + x_bytes + static_cast<size_t>(p.stages) * stage_bytes + kBarrierBytes;
@@ -1038,8 +1044,12 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
         p.lists = reinterpret_cast<uint64_t*>(lists);
         p.counts = reinterpret_cast<int*>(aux);
         IVR_CUDA(cudaMemsetAsync(p.counts, 0, static_cast<size_t>(pl.n_lists) * p.nq_pad * 4, st));
-        IVR_TRY(pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
-                          : launch_cluster(search_mma_xres_kernel<0>, tmq, tmx, p, pl.grid, 2, pl.smem, st));
+        int rc;
+        if (p.tn == 256) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 256>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                        : launch_cluster(search_mma_xres_kernel<0, 256>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        else             rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                        : launch_cluster(search_mma_xres_kernel<0, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        IVR_TRY(rc);
         in->entries = p.lists; in->counts = p.counts;
         in->list_stride = static_cast<int64_t>(p.nq_pad) * p.C; in->q_stride = p.C;
         in->cnt_list_stride = p.nq_pad; in->cnt_q_stride = 1;
@@ -1077,11 +1087,12 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const int mq = kTileQ * (xres ? 2 : cg);
     const int tq = static_cast<int>((nq + mq - 1) / mq);
     const int64_t nq_pad = static_cast<int64_t>(tq) * mq;
-    const int64_t nt = (idx->ntotal + kTileN - 1) / kTileN;
+    const int tile_rows = xres ? xres_tile_rows(idx) : kTileN;     // both phases use the same tile size
+    const int64_t nt = (idx->ntotal + tile_rows - 1) / tile_rows;
     // phase split (in row tiles): prefix = 1/16 of the rows, clamped to [256k, 2M] rows
     int64_t ntA = 0;
     if (env_int("IVR_MMA_TWO_PHASE", 1)) {
-        const int64_t lo = (256 << 10) / kTileN, hi = (2048 << 10) / kTileN;
+        const int64_t lo = (256 << 10) / tile_rows, hi = (2048 << 10) / tile_rows;
         ntA = std::min(std::max(nt / 16, lo), hi);
         if (ntA * 4 > nt) ntA = 0;                                 // small shard: single phase
     }
@@ -1093,7 +1104,8 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         // the short prefix phase has to learn its thresholds from scratch: the query-tile-resident kernel
         // (few, long candidate streams) does that better, so it is used for the prefix whenever the
         // layouts agree (CTA pairs, one query tile per pair available)
-        const bool prefix_qres = xres && n_phases == 2 && ph == 0 && cg == 2 && tq <= idx->sm_count / 2;
+        const bool prefix_qres = xres && n_phases == 2 && ph == 0 && cg == 2 && tq <= idx->sm_count / 2 &&
+                                 tile_rows == kTileN;
         IVR_TRY((xres && !prefix_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
     }
     size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
@@ -1137,7 +1149,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     if (timed) cudaEventRecord(idx->ev[5], st);
 
     // TMA descriptors (the row descriptor is cached until the matrix moves or grows)
-    const int box_rows = kTileN / (xres ? 2 : cg);
+    const int box_rows = tile_rows / (xres ? 2 : cg);
     CUtensorMap tmq;
     IVR_TRY(make_tmap(&tmq, q_h, nq_pad, idx->dpad, kTileQ));
     if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != box_rows) {
@@ -1190,7 +1202,8 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // measured (4096 queries, k=100, two-phase): 10 M rows 36.5 ms query-tile-resident vs 37.6 ms
     // row-tile-resident; 12.5 M 44.2 vs 43.0; 25 M 97.1 vs 85.3; 100 M 405 vs 331 -- the row-tile-resident
     // kernel moves 9x fewer bytes (the GPU is power-capped), so it takes over from ~12 M rows
-    const bool xres = (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
+    const bool wide = idx->dpad > kMaxKBlocks * kKBlock;           // 513..1024 dims: only the row-tile-resident kernel fits
+    const bool xres = wide || (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
                                       idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 12)) * 1000000);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group

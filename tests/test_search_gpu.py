@@ -63,7 +63,7 @@ def cta_group(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("d", [512, 384, 64, 100])
+@pytest.mark.parametrize("d", [512, 384, 64, 100, 768, 1024])
 @pytest.mark.parametrize("nq", [5, 128, 300])
 def test_mma_path_dims_and_batches(d, nq, cta_group):
     xb = synth.clip_like(30000, d, seed=61, n_centres=256)
@@ -131,6 +131,16 @@ def test_mma_two_phase_large_shard(mode, monkeypatch):
     monkeypatch.setenv("IVR_MMA_TWO_PHASE", "0")                 # single phase must give the same ids/scores
     D1, I1 = check(idx, ref, xq, 100, path=2)
     assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+
+
+def test_mma_vit_l14_768d_batch():
+    """768-d (CLIP ViT-L/14, the reference's configured model) on the batched path: 128-row tiles."""
+    xb = synth.clip_like(60_000, 768, seed=75, n_centres=128)
+    xq = synth.clip_like(700, 768, seed=76, n_centres=128)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=0)
+    t = idx.last_timing()
+    assert t["path"] == "mma" and t["kernel"] == "search_mma_xres_kernel"
 
 
 def test_mma_and_stream_paths_agree():
