@@ -240,7 +240,11 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
     int use = path;
     // measured on B200 (10 M x 512): the streaming kernel wins for 1-2 queries (1.5 ms vs 1.7 ms), the
     // tcgen05 kernel from 3 queries up (2.1 ms vs 3.8 ms at 4 queries)
-    if (use == IVR_PATH_AUTO) use = (nq > 2 && mma_supported(idx, nq, k)) ? IVR_PATH_MMA : IVR_PATH_STREAM;
+    // auto: one query streams on the SIMT kernel; from two queries up the tcgen05 kernels win (measured at
+    // 1 M .. 100 M rows, 512 / 768 dims) -- unless only the batched kernels fit the shape, which pay off from three
+    if (use == IVR_PATH_AUTO)
+        use = ((nq >= 2 && mma_small_supported(idx, nq, k)) || (nq > 2 && mma_supported(idx, nq, k))) ? IVR_PATH_MMA
+                                                                                                     : IVR_PATH_STREAM;
     if (use == IVR_PATH_MMA) {
         if (!mma_supported(idx, nq, k)) {
             set_error("search: the tcgen05 path does not support dim=%d k=%d", idx->dim, k);

@@ -56,6 +56,7 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
 int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
                int64_t* I_dev, int64_t id_offset, cudaStream_t st);
 bool mma_supported(const ivr_index* idx, int64_t nq, int k);
+bool mma_small_supported(const ivr_index* idx, int64_t nq, int k);   // small-batch kernel (search_mma_small.cu)
 
 // Generic list merge.  For query q, list l lives at entries + l*list_stride + q*q_stride
 // (64-bit keys) and holds counts[l*cnt_list_stride + q*cnt_q_stride] entries (or

@@ -133,6 +133,115 @@ def test_mma_two_phase_large_shard(mode, monkeypatch):
     assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
 
 
+@pytest.fixture
+def small_kernel(monkeypatch):
+    """Force the small-batch (operand-swapped, row-streaming) tcgen05 kernel."""
+    monkeypatch.setenv("IVR_MMA_MODE", "3")
+
+
+@pytest.mark.parametrize("d", [512, 768, 1024, 384, 100, 64])
+@pytest.mark.parametrize("nq", [1, 2, 5, 16, 17, 33, 64])
+def test_small_kernel_dims_and_batches(d, nq, small_kernel):
+    xb = synth.clip_like(30000, d, seed=81, n_centres=256)
+    xq = synth.clip_like(nq, d, seed=82, n_centres=256)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=2)
+    t = idx.last_timing()
+    assert t["path"] == "mma" and t["kernel"] == "search_mma_small_kernel"
+
+
+@pytest.mark.parametrize("d,nq", [(512, 128), (512, 100), (768, 80), (256, 128), (64, 97)])
+def test_small_kernel_widest_batches(d, nq, small_kernel):
+    xb = synth.clip_like(25000, d, seed=83, n_centres=128)
+    xq = synth.clip_like(nq, d, seed=84, n_centres=128)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=2)
+    assert idx.last_timing()["kernel"] == "search_mma_small_kernel"
+
+
+@pytest.mark.parametrize("n", [1, 100, 127, 128, 129, 1000, 5000, 19001])
+def test_small_kernel_small_indexes(n, small_kernel):
+    xb = synth.gaussian_unit(n, 128, seed=85 + n)
+    xq = synth.gaussian_unit(37, 128, seed=86)
+    idx, ref = build(xb)
+    D, I = check(idx, ref, xq, 100, path=2)
+    if n < 100:
+        assert (I[:, n:] == -1).all()
+
+
+@pytest.mark.parametrize("k", [1, 10, 100, 128])
+def test_small_kernel_k_values(k, small_kernel):
+    xb = synth.clip_like(40000, 128, seed=87, n_centres=64)
+    xq = synth.clip_like(48, 128, seed=88, n_centres=64)
+    idx, ref = build(xb)
+    check(idx, ref, xq, k, path=2)
+
+
+def test_small_kernel_unsupported_shapes_fall_back_in_auto_mode_and_fail_loudly_when_forced(monkeypatch):
+    import ivr_b200
+    xb = synth.clip_like(20000, 128, seed=89, n_centres=64)
+    xq = synth.clip_like(8, 128, seed=90, n_centres=64)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 300, path=2)                              # k > 128: the batched kernel takes it
+    assert idx.last_timing()["kernel"] == "search_mma_kernel"
+    monkeypatch.setenv("IVR_MMA_MODE", "3")
+    with pytest.raises(ivr_b200._native.NativeError):
+        idx.search(xq, 300)
+
+
+@pytest.mark.parametrize("ratio", [0, 2], ids=["two_launches", "three_launches"])
+def test_small_kernel_seeded_launches_match_single_launch(ratio, small_kernel, monkeypatch):
+    """Shards of >= 4 tiles per SM are searched in 2-3 launches, each seeding the next one's thresholds."""
+    if ratio:
+        monkeypatch.setenv("IVR_MMA_SMALL_RATIO", str(ratio))
+    xb = synth.clip_like(300_000, 64, seed=91, n_centres=512)
+    xq = synth.clip_like(24, 64, seed=92, n_centres=512)
+    idx, ref = build(xb)
+    D2, I2 = check(idx, ref, xq, 100, path=2)
+    n_launches = idx.last_timing()["score_launches"]
+    assert n_launches == (3 if ratio else 2)
+    monkeypatch.setenv("IVR_MMA_TWO_PHASE", "0")
+    D1, I1 = check(idx, ref, xq, 100, path=2)
+    assert idx.last_timing()["score_launches"] == 1
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+
+
+def test_small_kernel_rising_scores_force_list_compaction(small_kernel, monkeypatch):
+    """Rows sorted by ASCENDING similarity to the queries: every row beats the current threshold, so the
+    candidate lists fill and compact over and over -- the worst case of the fused top-k."""
+    monkeypatch.setenv("IVR_MMA_TWO_PHASE", "0")
+    rng = np.random.default_rng(93)
+    d, n = 64, 120_000
+    q = synth.gaussian_unit(4, d, seed=94)
+    alpha = np.linspace(0.0, 3.0, n, dtype=np.float32)[:, None]
+    xb = rng.standard_normal((n, d), dtype=np.float32) * 0.3 + alpha * q.mean(axis=0, keepdims=True) * np.sqrt(d)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    idx, ref = build(np.ascontiguousarray(xb, dtype=np.float32))
+    check(idx, ref, q, 100, path=2)
+    check(idx, ref, q[:1], 128, path=2)
+
+
+def test_small_kernel_ties_and_duplicates(small_kernel):
+    base = synth.gaussian_unit(50, 64, seed=95)
+    xb = np.concatenate([base] * 40)
+    idx, ref = build(xb)
+    check(idx, ref, base[:20], 100, path=2)
+    xb = synth.gaussian_unit(60_000, 512, seed=0)
+    xq = synth.gaussian_unit(60, 512, seed=1)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 100, path=2)
+
+
+def test_auto_mode_uses_the_small_kernel_for_small_batches():
+    xb = synth.clip_like(50_000, 512, seed=96, n_centres=128)
+    idx, ref = build(xb)
+    for nq, kern in [(1, "search_stream_kernel"), (16, "search_mma_small_kernel"), (64, "search_mma_small_kernel"),
+                     (300, "search_mma_kernel")]:
+        xq = synth.clip_like(nq, 512, seed=97 + nq, n_centres=128)
+        check(idx, ref, xq, 100, path=0)
+        assert idx.last_timing()["kernel"] == kern, (nq, idx.last_timing())
+
+
 def test_mma_vit_l14_768d_batch():
     """768-d (CLIP ViT-L/14, the reference's configured model) on the batched path: 128-row tiles."""
     xb = synth.clip_like(60_000, 768, seed=75, n_centres=128)
