@@ -145,10 +145,11 @@ __device__ __forceinline__ float warp_compact_topk(uint64_t* list, int cnt, int 
 }
 
 // Large-k variant (capacity C > 512): the same contract, but the sort runs in place in
-// memory (warp-wide bitonic network over `cap` slots, cap a power of two) instead of in
-// registers.  Slow and rare: it exists so that k up to IVR_MAX_K stays exact.
-static __device__ __noinline__ float warp_compact_topk_mem(uint64_t* list, int cnt, int k, int cap, int lane) {
-    for (int g = cnt + lane; g < cap; g += 32) list[g] = 0ull;
+// memory (warp-wide bitonic network over `cap` slots, cap a power of two, `stride` entries apart)
+// instead of in registers.  Slow and rare: it exists so that k up to IVR_MAX_K stays exact.
+static __device__ __noinline__ float warp_compact_topk_mem(uint64_t* list, int cnt, int k, int cap, int lane,
+                                                           int stride = 1) {
+    for (int g = cnt + lane; g < cap; g += 32) list[static_cast<int64_t>(g) * stride] = 0ull;
     __syncwarp();
     for (int s = 2; s <= cap; s <<= 1) {
         for (int t = s >> 1; t >= 1; t >>= 1) {
@@ -156,13 +157,13 @@ static __device__ __noinline__ float warp_compact_topk_mem(uint64_t* list, int c
                 const int lo = 2 * i - (i & (t - 1));
                 const int hi = lo + t;
                 const bool desc = (lo & s) == 0;
-                const uint64_t a = list[lo], b = list[hi];
-                if ((a < b) == desc) { list[lo] = b; list[hi] = a; }
+                const uint64_t a = list[static_cast<int64_t>(lo) * stride], b = list[static_cast<int64_t>(hi) * stride];
+                if ((a < b) == desc) { list[static_cast<int64_t>(lo) * stride] = b; list[static_cast<int64_t>(hi) * stride] = a; }
             }
             __syncwarp();
         }
     }
-    const uint64_t kth = list[k - 1];
+    const uint64_t kth = list[static_cast<int64_t>(k - 1) * stride];
     __syncwarp();
     return (cnt >= k) ? key_score(kth) : __int_as_float(0xff800000);
 }

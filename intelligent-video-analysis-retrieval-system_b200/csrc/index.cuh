@@ -69,6 +69,8 @@ struct MergeIn {
     int     n_lists;
     int     fixed_count;
     int     raw;             // entries are raw {score bits, row} pairs (converted to keys on load)
+    int     interleave;      // lists of 32 consecutive queries are interleaved: entry i of query q lives at
+                             // l*list_stride + (q / 32) * q_stride * 32 + i * 32 + q % 32
 };
 // final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset;
 // scores are multiplied by q_scale[q] when q_scale != nullptr (power-of-two query scaling)

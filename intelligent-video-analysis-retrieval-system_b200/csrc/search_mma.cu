@@ -36,7 +36,8 @@
 namespace ivr {
 
 
-// One 32-column chunk of one query's scores (v) against its admission threshold.  Sub-maxima of
+// One 32-column chunk of one query's scores (v) against its admission threshold; survivors go to the
+// thread's candidate list (entry i at my_list[i * 32]: the lists of a warp are interleaved).  Sub-maxima of
 // the four 8-column groups are formed with independent 3-input max trees (short dependency
 // chains); a warp vote per group skips groups without survivors, so the common "one survivor in
 // the whole warp-chunk" case costs 8 predicated stores instead of 32.
@@ -58,7 +59,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float tau,
 #pragma unroll
             for (int i = 8 * g; i < 8 * g + 8; ++i) {                  // branch-free: predicated 8-byte store
                 const float sc = __uint_as_float(v[i]);
-                uint64_t* dst = my_list + cnt;
+                uint64_t* dst = my_list + static_cast<int64_t>(cnt) * kListStride;
                 asm volatile(
                     "{\n\t.reg .pred pp;\n\tsetp.gt.f32 pp, %0, %1;\n\t"
                     "@pp st.global.v2.b32 [%2], {%3, %4};\n\t}"
@@ -70,7 +71,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float tau,
         for (int i = 0; i < 32; ++i) {
             const float sc = __uint_as_float(v[i]);
             if (sc > tau && col0 + i < nvalid) {
-                my_list[cnt] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
+                my_list[static_cast<int64_t>(cnt) * kListStride] = static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(rowc + i) << 32);
                 ++cnt;
             }
         }
@@ -96,11 +97,10 @@ struct MmaParams {
     int     segs_max;        // max query tiles one group touches
     uint64_t row_policy;     // L2 eviction priority of the row-tile loads
     int      skip_epilogue;  // debug/perf probe: drain nothing (results are garbage)
-    uint64_t* lists;         // [grid CTAs][segs_max][2 sets][128][C] raw candidate lists
-    int2*     state;         // [grid CTAs][segs_max][2 sets][128] {cnt, tau bits}
+    uint64_t* lists;         // [slots][nq_pad / 32][C][32] raw candidate lists, interleaved per warp
+    int*      counts;        // [slots][nq_pad]
+    int2*     state;         // [grid CTAs][segs_max][2 sets][128] {cnt, tau bits} of a parked segment
     uint32_t* tau_g;         // [nq_pad] order-preserving encoding of the shared per-query threshold
-    uint64_t* out_keys;      // [slots][nq_pad][k]
-    int*      out_counts;    // [slots][nq_pad]
 };
 
 // The unit enumeration shared by all warp roles.
@@ -278,26 +278,36 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int quarter = warp & 3;                              // TMEM lanes [32*quarter, +32)
         const int r = quarter * 32 + lane;                         // query row inside this CTA's tile
         const float NEG_INF = __int_as_float(0xff800000), POS_INF = __int_as_float(0x7f800000);
-        auto list_base = [&](int s, int row) {
-            return p.lists + (((static_cast<int64_t>(blockIdx.x) * p.segs_max + s) * 2 + set) * kTileQ + row) * p.C;
-        };
         auto state_ptr = [&](int s) {
             return p.state + ((static_cast<int64_t>(blockIdx.x) * p.segs_max + s) * 2 + set) * kTileQ + r;
         };
         for (int s = 0; s < p.segs_max; ++s) *state_ptr(s) = make_int2(0, __float_as_int(NEG_INF));
+        // list slot of this group for query tile t: the c grid groups first, then the leftover groups that touch t
+        auto slot_of = [&](int t) {
+            if (group < p.g_grid) return group / p.tq;
+            const int Gl = p.groups - p.g_grid;
+            const int64_t ntl = p.nt - p.ntg, Ul = static_cast<int64_t>(p.tq) * ntl;
+            const int glmin = static_cast<int>(((static_cast<int64_t>(t) * ntl + 1) * Gl - 1) / Ul);
+            return p.c + (group - p.g_grid - glmin);
+        };
 
         int cnt = 0; float tau = NEG_INF; int64_t q_global = 0; bool q_ok = false;
-        uint64_t* my_list = nullptr; uint64_t* warp_lists = nullptr;
+        uint64_t* my_list = nullptr; int* my_count = nullptr;
 
-        auto compact_lane = [&](int l) {                           // all lanes call; list of lane l
-            const int c_l = __shfl_sync(0xffffffffu, cnt, l);
-            __syncwarp();
-            const float t_l = warp_compact_raw<E>(warp_lists + static_cast<int64_t>(l) * p.C, c_l, p.k, p.C, lane);
-            if (lane == l) {
-                cnt = min(cnt, p.k);
-                if (t_l > tau) tau = t_l;
-                if (q_ok && cnt >= p.k) atomicMax(p.tau_g + q_global, f2ord(t_l));   // share with the other CTAs
+        // make room for two more chunks (<= 64 entries): all 32 lists of the warp are pruned together
+        auto make_room = [&]() {
+            if (!__any_sync(0xffffffffu, cnt > p.C - 64)) return;
+            const float tau_before = tau;
+            unsigned bad = warp_prune_lists(my_list, cnt, tau, p.k);
+            bad |= __ballot_sync(0xffffffffu, cnt > p.C - 64);      // no pivot / no progress (ties): exact compaction
+            while (bad) {
+                const int l = __ffs(bad) - 1; bad &= bad - 1;
+                const int c_l = __shfl_sync(0xffffffffu, cnt, l);
+                __syncwarp();
+                const float t_l = warp_compact_raw<E>(my_list - lane + l, c_l, p.k, p.C, lane, kListStride);
+                if (lane == l) { cnt = min(cnt, p.k); tau = fmaxf(tau, t_l); }
             }
+            if (q_ok && tau > tau_before) atomicMax(p.tau_g + q_global, f2ord(tau));   // share with the other CTAs
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
             if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
@@ -312,8 +322,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 cnt = st.x;
                 tau = q_ok ? __int_as_float(st.y) : POS_INF;        // padded queries admit nothing
                 if (q_ok) tau = fmaxf(tau, ord2f(__ldcg(p.tau_g + q_global)));
-                warp_lists = list_base(s, quarter * 32);
-                my_list = warp_lists + static_cast<int64_t>(lane) * p.C;
+                const int64_t slot = static_cast<int64_t>(slot_of(t)) * 2 + set;
+                my_list = p.lists + (slot * p.nq_pad + (q_global - lane)) * p.C + lane;
+                my_count = p.counts + slot * p.nq_pad + q_global;
             },
             [&](int, int, int64_t j, int64_t n) {
                 if (static_cast<int>(n & 1) != set) return;
@@ -331,9 +342,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
                 for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : kTileN / 32); c += 2) {
-                    // make room: two chunks can add up to 64 entries to one list
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
-                    while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
+                    make_room();
                     tmem_wait_ld(va);
                     tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                     process_chunk(va, c, row0, nvalid);
@@ -350,47 +359,10 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     else mbar_arrive_cluster(tempty_bar(set), 0);
                 }
             },
-            [&](int s, int, int, bool) {                            // visit end: park the state
+            [&](int s, int, int, bool) {                            // visit end: park the state, publish the count
                 *state_ptr(s) = make_int2(cnt, __float_as_int(tau));
+                *my_count = cnt;                                    // the merge kernel reads the raw list directly
             });
-
-        // final: every (segment, set) list -> sorted top-k keys in its output slot.  Slots of a query
-        // tile: the c grid groups first, then the leftover groups that touch it.
-        {
-            int t_first, nseg, slot0_first;
-            if (group < p.g_grid) {
-                t_first = group % p.tq; nseg = (group / p.tq < p.ntg) ? 1 : 0; slot0_first = group / p.tq;
-            } else {
-                const LeftRange lr(p, group);
-                t_first = lr.t_first; nseg = lr.nseg; slot0_first = -1;
-            }
-            for (int s = 0; s < nseg; ++s) {
-                const int t = t_first + s;
-                int slot_g = slot0_first;
-                if (slot_g < 0) {                                   // leftover: index among the leftover groups of t
-                    const int Gl = p.groups - p.g_grid;
-                    const int64_t ntl = p.nt - p.ntg, Ul = static_cast<int64_t>(p.tq) * ntl;
-                    const int glmin = static_cast<int>(((static_cast<int64_t>(t) * ntl + 1) * Gl - 1) / Ul);
-                    slot_g = p.c + (group - p.g_grid - glmin);
-                }
-                const int slot = slot_g * 2 + set;
-                const int2 st = *state_ptr(s);
-                const int64_t qg = static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r;
-                uint64_t* wl = list_base(s, quarter * 32);
-                for (int l = 0; l < 32; ++l) {
-                    const int c_l = __shfl_sync(0xffffffffu, st.x, l);
-                    const int64_t q_l = __shfl_sync(0xffffffffu, qg, l);
-                    if (c_l == 0 || q_l >= p.nq) continue;          // warp-uniform
-                    uint64_t* lst = wl + static_cast<int64_t>(l) * p.C;
-                    __syncwarp();
-                    warp_compact_raw<E>(lst, c_l, p.k, p.C, lane);
-                    const int keep = min(c_l, p.k);
-                    uint64_t* dst = p.out_keys + (static_cast<int64_t>(slot) * p.nq_pad + q_l) * p.k;
-                    for (int i = lane; i < keep; i += 32) dst[i] = raw_to_key(lst[i]);
-                    if (lane == 0) p.out_counts[static_cast<int64_t>(slot) * p.nq_pad + q_l] = keep;
-                }
-            }
-        }
     }
 
     // ------------------------------------------------------------------ teardown ----
@@ -422,7 +394,7 @@ struct XresParams {
     int     tn;              // rows per tile (256 or 128)
     int     groups;          // CTA pairs
     int     nq_pad;          // tq * 256
-    uint64_t* lists;         // [groups][2 sets][nq_pad][C] raw candidate lists
+    uint64_t* lists;         // [groups][2 sets][nq_pad / 32][C][32] raw candidate lists, interleaved per warp
     int*      counts;        // [groups][2 sets][nq_pad]
     uint32_t* tau_g;         // [nq_pad] shared per-query threshold (order-preserving encoding)
     uint64_t  row_policy;
@@ -550,20 +522,25 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const float POS_INF = __int_as_float(0x7f800000);
         const int64_t set_base = (static_cast<int64_t>(group) * 2 + set) * p.nq_pad;
         int cnt = 0; float tau = 0.f; int64_t q_global = 0; bool q_ok = false;
-        uint64_t* my_list = nullptr; uint64_t* warp_lists = nullptr;
+        uint64_t* my_list = nullptr;
         // state of this set's NEXT unit, prefetched while the current one is processed
         int64_t pf_n = -1; int pf_cnt = 0; uint32_t pf_tau = 0;
         auto q_of = [&](int t) { return static_cast<int64_t>(t) * (kTileQ * CG) + cta_rank * kTileQ + r; };
 
-        auto compact_lane = [&](int l) {
-            const int c_l = __shfl_sync(0xffffffffu, cnt, l);
-            __syncwarp();
-            const float t_l = warp_compact_raw<E>(warp_lists + static_cast<int64_t>(l) * p.C, c_l, p.k, p.C, lane);
-            if (lane == l) {
-                cnt = min(cnt, p.k);
-                if (t_l > tau) tau = t_l;
-                if (q_ok && cnt >= p.k) atomicMax(p.tau_g + q_global, f2ord(t_l));
+        // make room for two more chunks (<= 64 entries): all 32 lists of the warp are pruned together
+        auto make_room = [&]() {
+            if (!__any_sync(0xffffffffu, cnt > p.C - 64)) return;
+            const float tau_before = tau;
+            unsigned bad = warp_prune_lists(my_list, cnt, tau, p.k);
+            bad |= __ballot_sync(0xffffffffu, cnt > p.C - 64);      // no pivot / no progress (ties): exact compaction
+            while (bad) {
+                const int l = __ffs(bad) - 1; bad &= bad - 1;
+                const int c_l = __shfl_sync(0xffffffffu, cnt, l);
+                __syncwarp();
+                const float t_l = warp_compact_raw<E>(my_list - lane + l, c_l, p.k, p.C, lane, kListStride);
+                if (lane == l) { cnt = min(cnt, p.k); tau = fmaxf(tau, t_l); }
             }
+            if (q_ok && tau > tau_before) atomicMax(p.tau_g + q_global, f2ord(tau));
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
             if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
@@ -582,8 +559,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             if (pf_n == n) { cnt = pf_cnt; tau = ord2f(pf_tau); }
             else { cnt = p.counts[idx]; tau = ord2f(__ldcg(p.tau_g + q_global)); }
             if (!q_ok) tau = POS_INF;                               // padded queries admit nothing
-            my_list = p.lists + idx * p.C;
-            warp_lists = my_list - static_cast<int64_t>(lane) * p.C;
+            my_list = p.lists + (idx - lane) * p.C + lane;       // interleaved: entry i at my_list[i * 32]
             int t2 = t + step_t; int64_t j2 = j + step_j;
             if (t2 >= p.tq) { t2 -= p.tq; ++j2; }
             if (n + 2 < n_units) {                                  // prefetch the state of unit n + 2
@@ -600,8 +576,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
             for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : TN / 32); c += 2) {
-                unsigned need = __ballot_sync(0xffffffffu, cnt > p.C - 64);
-                while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact_lane(l); }
+                make_room();
                 tmem_wait_ld(va);
                 tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                 process_chunk(va, c, row0, nvalid);
@@ -740,9 +715,8 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
     }
     pl->xres = false; pl->cg = cg; pl->grid = grid; pl->E = (C == 256) ? 8 : 0;
     pl->n_lists = 2 * (p.c + left_per_tile);                       // output slots per query
-    pl->list_bytes = static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * C * 8;
+    pl->list_bytes = static_cast<size_t>(pl->n_lists) * p.nq_pad * C * 8;
     pl->aux_bytes = static_cast<size_t>(grid) * p.segs_max * 2 * kTileQ * sizeof(int2) + 256 +
-                    static_cast<size_t>(pl->n_lists) * p.nq_pad * k * 8 + 256 +
                     static_cast<size_t>(pl->n_lists) * p.nq_pad * 4 + 256;
     return IVR_OK;
 }
@@ -817,7 +791,7 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
         in->entries = p.lists; in->counts = p.counts;
         in->list_stride = static_cast<int64_t>(p.nq_pad) * p.C; in->q_stride = p.C;
         in->cnt_list_stride = p.nq_pad; in->cnt_q_stride = 1;
-        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 1;
+        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 1; in->interleave = 1;
     } else {
         MmaParams& p = pl.q;
         p.tau_g = tau_g;
@@ -825,19 +799,18 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return aux + o; };
         p.state = reinterpret_cast<int2*>(carve(static_cast<size_t>(pl.grid) * p.segs_max * 2 * kTileQ * sizeof(int2)));
-        p.out_keys = reinterpret_cast<uint64_t*>(carve(static_cast<size_t>(pl.n_lists) * p.nq_pad * k * 8));
-        p.out_counts = reinterpret_cast<int*>(carve(static_cast<size_t>(pl.n_lists) * p.nq_pad * 4));
-        IVR_CUDA(cudaMemsetAsync(p.out_counts, 0, static_cast<size_t>(pl.n_lists) * p.nq_pad * 4, st));
+        p.counts = reinterpret_cast<int*>(carve(static_cast<size_t>(pl.n_lists) * p.nq_pad * 4));
+        IVR_CUDA(cudaMemsetAsync(p.counts, 0, static_cast<size_t>(pl.n_lists) * p.nq_pad * 4, st));
         int rc;
         if (pl.cg == 2) rc = pl.E == 8 ? launch_cluster(search_mma_kernel<2, 8>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
                                        : launch_cluster(search_mma_kernel<2, 0>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         else            rc = pl.E == 8 ? launch_cluster(search_mma_kernel<1, 8>, tmq, tmx, p, pl.grid, 1, pl.smem, st)
                                        : launch_cluster(search_mma_kernel<1, 0>, tmq, tmx, p, pl.grid, 1, pl.smem, st);
         IVR_TRY(rc);
-        in->entries = p.out_keys; in->counts = p.out_counts;
-        in->list_stride = static_cast<int64_t>(p.nq_pad) * k; in->q_stride = k;
+        in->entries = p.lists; in->counts = p.counts;
+        in->list_stride = static_cast<int64_t>(p.nq_pad) * p.C; in->q_stride = p.C;
         in->cnt_list_stride = p.nq_pad; in->cnt_q_stride = 1;
-        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 0;
+        in->n_lists = pl.n_lists; in->fixed_count = 0; in->raw = 1; in->interleave = 1;
     }
     return IVR_OK;
 }
@@ -853,24 +826,29 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const int64_t nq_pad = static_cast<int64_t>(tq) * mq;
     const int tile_rows = xres ? xres_tile_rows(idx) : kTileN;     // both phases use the same tile size
     const int64_t nt = (idx->ntotal + tile_rows - 1) / tile_rows;
-    // phase split (in row tiles): prefix = 1/16 of the rows, clamped to [256k, 2M] rows
-    int64_t ntA = 0;
+    // Launch boundaries (in row tiles).  The first launch covers a small prefix (IVR_MMA_PHASE0_ROWS, 32k
+    // rows), every further one IVR_MMA_PHASE_RATIO (16) times the rows seen so far, the last one the rest:
+    // a launch admits ~k * ratio candidates per query instead of re-learning its thresholds in every list.
+    constexpr int kMaxPhases = 6;
+    int64_t bounds[kMaxPhases + 1] = {0};
+    int n_phases = 0;
     if (env_int("IVR_MMA_TWO_PHASE", 1)) {
-        const int64_t lo = (256 << 10) / tile_rows, hi = (2048 << 10) / tile_rows;
-        ntA = std::min(std::max(nt / 16, lo), hi);
-        if (ntA * 4 > nt) ntA = 0;                                 // small shard: single phase
+        const int64_t ratio = std::max(2, env_int("IVR_MMA_PHASE_RATIO", 16));
+        int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 32768) / tile_rows);
+        while (n_phases < kMaxPhases - 1 && b * 2 <= nt) {         // a boundary must leave at least as much for later
+            bounds[++n_phases] = b;
+            b *= ratio;
+        }
     }
-    const int n_phases = ntA > 0 ? 2 : 1;
-    Plan plan[2];
+    bounds[++n_phases] = nt;
+    Plan plan[kMaxPhases];
     for (int ph = 0; ph < n_phases; ++ph) {
-        const int64_t t0 = (ph == 0) ? 0 : ntA;
-        const int64_t n = (n_phases == 1) ? nt : (ph == 0 ? ntA : nt - ntA);
-        // the short prefix phase has to learn its thresholds from scratch: the query-tile-resident kernel
-        // (few, long candidate streams) does that better, so it is used for the prefix whenever the
-        // layouts agree (CTA pairs, one query tile per pair available)
-        const bool prefix_qres = xres && n_phases == 2 && ph == 0 && cg == 2 && tq <= idx->sm_count / 2 &&
-                                 tile_rows == kTileN;
-        IVR_TRY((xres && !prefix_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
+        const int64_t t0 = bounds[ph], n = bounds[ph + 1] - bounds[ph];
+        // the early launches have to learn their thresholds from scratch: the query-tile-resident kernel
+        // (few, long candidate streams per query) does that better, so it runs every launch but the last
+        // whenever the layouts agree (CTA pairs, one query tile per pair available, 256-row tiles)
+        const bool early_qres = xres && ph + 1 < n_phases && cg == 2 && tq <= idx->sm_count / 2 && tile_rows == kTileN;
+        IVR_TRY((xres && !early_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
     }
     size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
     for (int ph = 0; ph < n_phases; ++ph) {
@@ -886,8 +864,8 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const size_t o_tg = carve(static_cast<size_t>(nq_pad) * 4);
     const size_t o_l  = carve(list_bytes);
     const size_t o_a  = carve(aux_bytes);
-    const size_t o_pk = carve(static_cast<size_t>(2) * nq * k * 8);      // per-phase merged keys [phase][nq][k]
-    const size_t o_pc = carve(static_cast<size_t>(2) * nq * 4);
+    const size_t o_pk = carve(static_cast<size_t>(n_phases) * nq * k * 8);   // per-launch merged keys [phase][nq][k]
+    const size_t o_pc = carve(static_cast<size_t>(n_phases) * nq * 4);
     const size_t tmp_keys = merge_tmp_entries(max_lists, nq, k);
     const size_t o_t  = carve(tmp_keys * 8);
     const size_t o_tc = carve((static_cast<size_t>(max_lists) * nq + 64) * 4);
@@ -930,18 +908,19 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         } else {
             IVR_TRY(merge_lists_keys(in, nq, k, ph_keys + static_cast<size_t>(ph) * nq * k,
                                      ph_counts + static_cast<size_t>(ph) * nq, tmp_e, tmp_c, st, &idx->launches[1]));
-            if (ph == 0) {
-                IVR_TRY(launch_seed_tau(ph_keys, ph_counts, tau_g, nq, k, st));
+            if (ph + 1 < n_phases) {                               // atomicMax: the seed can only rise
+                IVR_TRY(launch_seed_tau(ph_keys + static_cast<size_t>(ph) * nq * k, ph_counts + static_cast<size_t>(ph) * nq,
+                                        tau_g, nq, k, st));
                 idx->launches[1]++;
             }
         }
     }
-    if (n_phases == 2) {
+    if (n_phases > 1) {
         if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
         MergeIn in{};
         in.entries = ph_keys; in.counts = ph_counts;
         in.list_stride = nq * k; in.q_stride = k; in.cnt_list_stride = nq; in.cnt_q_stride = 1;
-        in.n_lists = 2; in.fixed_count = 0; in.raw = 0;
+        in.n_lists = n_phases; in.fixed_count = 0; in.raw = 0;
         IVR_TRY(merge_lists_final(in, nq, k, D_dev, I_dev, id_offset, tmp_e, tmp_c, st, &idx->launches[1], q_scale));
     }
     if (timed) {

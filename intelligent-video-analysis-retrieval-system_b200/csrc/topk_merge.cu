@@ -31,9 +31,11 @@ __device__ __forceinline__ void for_each_key(const MergeIn& in, int64_t q, int l
     for (int l = l0 + warp; l < l1; l += nwarps) {
         const int cnt = in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride]
                                   : in.fixed_count;
-        const uint64_t* base = in.entries + l * in.list_stride + q * in.q_stride;
+        const uint64_t* base = in.entries + l * in.list_stride +
+                               (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+        const int es = in.interleave ? 32 : 1;
         for (int i = lane; i < cnt; i += 32) {
-            uint64_t key = base[i];
+            uint64_t key = base[static_cast<int64_t>(i) * es];
             if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
             if (key != 0ull) f(key);
         }
