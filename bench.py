@@ -447,8 +447,9 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                     "traffic": measured_traffic(launches["kernel"], n_local, dim, nq, k), "kernel": launches["kernel"],
                     "kernel_ms": k_ms, "peak_source": src, "algorithmic_flops_per_launch": flops,
-                    "note": "kernel_ms brackets the whole scoring stage of one search: prefix launch "
-                            "(search_mma_kernel, ~4 %), inter-phase merges (<0.3 %) and the bulk launch"}
+                    "note": "kernel_ms brackets the whole scoring stage of one search: the short threshold-seeding "
+                            "launches (search_mma_kernel over 32k, 256k, 2M rows; ~3 %), their merges (<0.3 %) and "
+                            "the bulk launch"}
     else:
         passes = (nq + 3) // 4
         byts = float(n_local) * dim * 2 * passes                 # fp16 rows streamed once per 4-query pass

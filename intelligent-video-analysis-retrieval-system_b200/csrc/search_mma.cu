@@ -833,7 +833,10 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     int64_t bounds[kMaxPhases + 1] = {0};
     int n_phases = 0;
     if (env_int("IVR_MMA_TWO_PHASE", 1)) {
-        const int64_t ratio = std::max(2, env_int("IVR_MMA_PHASE_RATIO", 16));
+        // the row-tile-resident kernel spreads a query over 148 lists that never fill up during one launch, so
+        // its thresholds only improve at launch boundaries: it gets more of them (measured, 10 M x 4096 queries:
+        // 34.0 ms at ratio 8 vs 35.5 ms at 16; the query-tile-resident kernel prefers 16: 8.4 vs 8.9 ms at 1024 queries)
+        const int64_t ratio = std::max(2, env_int("IVR_MMA_PHASE_RATIO", xres ? 8 : 16));
         int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 32768) / tile_rows);
         while (n_phases < kMaxPhases - 1 && b * 2 <= nt) {         // a boundary must leave at least as much for later
             bounds[++n_phases] = b;
@@ -847,7 +850,9 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         // the early launches have to learn their thresholds from scratch: the query-tile-resident kernel
         // (few, long candidate streams per query) does that better, so it runs every launch but the last
         // whenever the layouts agree (CTA pairs, one query tile per pair available, 256-row tiles)
-        const bool early_qres = xres && ph + 1 < n_phases && cg == 2 && tq <= idx->sm_count / 2 && tile_rows == kTileN;
+        // -- and the launch is short (<= 3 M rows: beyond that re-reading the rows per query tile costs more)
+        const bool early_qres = xres && ph + 1 < n_phases && cg == 2 && tq <= idx->sm_count / 2 && tile_rows == kTileN &&
+                                n * tile_rows <= 3000000;
         IVR_TRY((xres && !early_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
     }
     size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
@@ -939,12 +944,13 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     const int cg = cta_group_mode();
     if (mode == 3 || (mode == 0 && nq <= env_int("IVR_MMA_SMALL_MAX_NQ", 128) && mma_small_supported(idx, nq, k)))
         return search_mma_small(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
-    // measured (4096 queries, k=100, two-phase): 10 M rows 36.5 ms query-tile-resident vs 37.6 ms
-    // row-tile-resident; 12.5 M 44.2 vs 43.0; 25 M 97.1 vs 85.3; 100 M 405 vs 331 -- the row-tile-resident
-    // kernel moves 9x fewer bytes (the GPU is power-capped), so it takes over from ~12 M rows
+    // measured (k=100, seeded launches): 4096 queries -- 3 M rows 11.6 ms query-tile-resident vs 11.5 ms
+    // row-tile-resident, 10 M 38.7 vs 34.0, 100 M 405 vs 325; 1024 queries -- 10 M 8.4 vs 9.6.  The
+    // row-tile-resident kernel moves 9x fewer bytes (the GPU is power-capped) but spreads a query over more
+    // candidate lists: it takes over from 2048 queries on >= 3 M rows and from 4 query tiles on >= 12 M rows
     const bool wide = idx->dpad > kMaxKBlocks * kKBlock;           // 513..1024 dims: only the row-tile-resident kernel fits
-    const bool xres = wide || (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 &&
-                                      idx->ntotal >= static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", 12)) * 1000000);
+    const int64_t xres_min_rows = static_cast<int64_t>(env_int("IVR_MMA_XRES_MIN_ROWS_M", nq >= 2048 ? 3 : 12)) * 1000000;
+    const bool xres = wide || (mode == 2) || (mode == 0 && nq > 3 * kTileQ * 2 && idx->ntotal >= xres_min_rows);
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
     idx->last_kernel = xres ? "search_mma_xres_kernel" : "search_mma_kernel";
