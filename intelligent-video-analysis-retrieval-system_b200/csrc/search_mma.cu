@@ -942,7 +942,10 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up on large shards.
     const int mode = env_int("IVR_MMA_MODE", 0);
     const int cg = cta_group_mode();
-    if (mode == 3 || (mode == 0 && nq <= env_int("IVR_MMA_SMALL_MAX_NQ", 128) && mma_small_supported(idx, nq, k)))
+    // measured (10 M rows): 512 dims -- 64 queries 2.0 ms small-batch vs 2.1 ms batched, 80: 2.5 vs 2.2, 128: 3.7 vs 2.3
+    // (the resident queries squeeze the row ring); 768 dims -- 64..80 queries 2.4-2.6 ms vs 5.7-6.2 ms
+    const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", idx->dpad <= kMaxKBlocks * kKBlock ? 64 : 128);
+    if (mode == 3 || (mode == 0 && nq <= small_max && mma_small_supported(idx, nq, k)))
         return search_mma_small(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
     // measured (k=100, seeded launches): 4096 queries -- 3 M rows 11.6 ms query-tile-resident vs 11.5 ms
     // row-tile-resident, 10 M 38.7 vs 34.0, 100 M 405 vs 325; 1024 queries -- 10 M 8.4 vs 9.6.  The
