@@ -162,6 +162,24 @@ IVR_API int ivr_dedup_fifo(int device, const float* e_host, int64_t n, int d,
                    const int64_t* scene_start, const int64_t* scene_end, int64_t n_scenes,
                    int fifo, float thr, uint8_t* keep_host);
 
+/* ------------------------------------------------------------------------
+ * Similar-sequence search
+ * ---------------------------------------------------------------------- */
+#define IVR_MAX_SEQ_LEN 128
+
+/* Replaces TemporalAnalyzer.find_similar_sequences (core.py:3644-3702, with
+ * _compute_sequence_similarity, core.py:3812-3832): for every target window start t in
+ * [0, nt - seq_len] and database window start j in [0, nd - seq_len], sim = float32 mean over i of
+ * cos(target[t+i], db[j+i]); windows with sim >= threshold are hits.  Host pointers; `target` is
+ * float32 [nt, dim], `db` float32 [nd, dim] (raw, un-normalised rows, as the reference passes them).
+ * Hits are written UNSORTED to hit_t / hit_j / hit_sim (capacity max_hits each; the host wrapper applies
+ * the reference's stable descending sort); *n_hits receives the total number of qualifying windows --
+ * when it exceeds max_hits only max_hits of them were stored and the caller retries with larger buffers.
+ * nt < seq_len or nd < seq_len yields zero hits (the reference returns [] there). */
+IVR_API int ivr_sequence_similarity(int device, const float* target_host, int64_t nt, const float* db_host,
+                            int64_t nd, int dim, int seq_len, float threshold, int64_t max_hits,
+                            int32_t* hit_t, int64_t* hit_j, float* hit_sim, int64_t* n_hits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from .frame_filter import FrameFilter                                 # noqa: F4
 from .relationships import build_similarity_relationships            # noqa: F401
 from .retriever import FAISSRetriever, KeyframeMetadata, SearchResult  # noqa: F401
 from .sharded import ShardedFlatIP                                    # noqa: F401
+from .temporal import TemporalAnalyzer                                # noqa: F401
 from .unified_builder import UnifiedBuilderIntegration, add_unified_index_support  # noqa: F401
 from .unified_index import (UnifiedIndex, UnifiedIndexConfig, create_optimized_index,  # noqa: F401
                             load_optimized_index)

@@ -66,6 +66,9 @@ PROTOTYPES = {
                                   C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "ivr_dedup_fifo": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "ivr_sequence_similarity": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                          C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_int64)]),
 }
 
 

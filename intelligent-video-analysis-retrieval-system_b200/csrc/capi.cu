@@ -33,6 +33,12 @@ int dedup_chain_device(const float* e_dev, int64_t n, int d, const int64_t* scen
                        const int64_t* scene_end_dev, int64_t n_scenes, int min_distance, float thr,
                        int force_last, int fifo, uint8_t* keep_dev, cudaStream_t st);
 
+int sequence_similarity_device(const float* target, int64_t nt, const float* db, int64_t nd, int dim, int seq_len,
+                               float thr, int64_t max_hits, int32_t* hit_t, int64_t* hit_j, float* hit_sim,
+                               unsigned long long* n_hits_dev, float* tn, float* dn, float* cblock,
+                               int64_t block_cols, cudaStream_t st);
+int64_t sequence_block_cols(int64_t nt, int64_t nd, int seq_len);
+
 static int require_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -481,6 +487,52 @@ int ivr_dedup_fifo(int device, const float* e_host, int64_t n, int d, const int6
                    const int64_t* scene_end, int64_t n_scenes, int fifo, float thr, uint8_t* keep_host) {
     return dedup_chain_host(device, e_host, n, d, scene_start, scene_end, n_scenes, 1, thr, 0, fifo, keep_host,
                             "dedup_fifo");
+}
+
+int ivr_sequence_similarity(int device, const float* target_host, int64_t nt, const float* db_host, int64_t nd,
+                            int dim, int seq_len, float threshold, int64_t max_hits, int32_t* hit_t, int64_t* hit_j,
+                            float* hit_sim, int64_t* n_hits) {
+    if (nt < 0 || nd < 0 || dim <= 0 || max_hits < 0 || !n_hits || (nt > 0 && !target_host) || (nd > 0 && !db_host) ||
+        (max_hits > 0 && (!hit_t || !hit_j || !hit_sim))) {
+        set_error("sequence_similarity: bad argument");
+        return IVR_EINVAL;
+    }
+    if (seq_len < 1 || seq_len > IVR_MAX_SEQ_LEN) {
+        set_error("sequence_similarity: seq_len %d outside 1..%d", seq_len, IVR_MAX_SEQ_LEN);
+        return IVR_EUNSUPPORTED;
+    }
+    if (nt - seq_len + 1 > 65535) {                                // one grid row per target window start
+        set_error("sequence_similarity: more than 65535 target windows (nt=%lld)", static_cast<long long>(nt));
+        return IVR_EUNSUPPORTED;
+    }
+    *n_hits = 0;
+    if (nt < seq_len || nd < seq_len) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const int64_t cols = sequence_block_cols(nt, nd, seq_len);
+    DevBuf t, d, tn, dn, cb, ht, hj, hs, cnt;
+    IVR_TRY(t.alloc(static_cast<size_t>(nt) * dim * 4)); IVR_TRY(d.alloc(static_cast<size_t>(nd) * dim * 4));
+    IVR_TRY(tn.alloc(static_cast<size_t>(nt) * dim * 4)); IVR_TRY(dn.alloc(static_cast<size_t>(nd) * dim * 4));
+    IVR_TRY(cb.alloc(static_cast<size_t>(nt) * cols * 4));
+    IVR_TRY(ht.alloc(std::max<size_t>(max_hits, 1) * 4)); IVR_TRY(hj.alloc(std::max<size_t>(max_hits, 1) * 8));
+    IVR_TRY(hs.alloc(std::max<size_t>(max_hits, 1) * 4)); IVR_TRY(cnt.alloc(8));
+    IVR_CUDA(cudaMemcpy(t.p, target_host, static_cast<size_t>(nt) * dim * 4, cudaMemcpyHostToDevice));
+    IVR_CUDA(cudaMemcpy(d.p, db_host, static_cast<size_t>(nd) * dim * 4, cudaMemcpyHostToDevice));
+    IVR_CUDA(cudaMemset(cnt.p, 0, 8));
+    IVR_TRY(sequence_similarity_device(static_cast<float*>(t.p), nt, static_cast<float*>(d.p), nd, dim, seq_len,
+                                       threshold, max_hits, static_cast<int32_t*>(ht.p), static_cast<int64_t*>(hj.p),
+                                       static_cast<float*>(hs.p), static_cast<unsigned long long*>(cnt.p),
+                                       static_cast<float*>(tn.p), static_cast<float*>(dn.p), static_cast<float*>(cb.p),
+                                       cols, nullptr));
+    unsigned long long total = 0;
+    IVR_CUDA(cudaMemcpy(&total, cnt.p, 8, cudaMemcpyDeviceToHost));
+    *n_hits = static_cast<int64_t>(total);
+    const size_t stored = static_cast<size_t>(std::min<unsigned long long>(total, static_cast<unsigned long long>(max_hits)));
+    if (stored) {
+        IVR_CUDA(cudaMemcpy(hit_t, ht.p, stored * 4, cudaMemcpyDeviceToHost));
+        IVR_CUDA(cudaMemcpy(hit_j, hj.p, stored * 8, cudaMemcpyDeviceToHost));
+        IVR_CUDA(cudaMemcpy(hit_sim, hs.p, stored * 4, cudaMemcpyDeviceToHost));
+    }
+    return IVR_OK;
 }
 
 }  // extern "C"

@@ -391,7 +391,7 @@ struct XresParams {
     int     nq, k, C, kblocks, stages, tq;
     int64_t nt;              // row tiles of this launch
     int64_t tile0;           // first row tile of this launch
-    int     tn;              // rows per tile (256 or 128)
+    int     tn;              // rows per tile (256, 192 or 128)
     int     groups;          // CTA pairs
     int     nq_pad;          // tq * 256
     uint64_t* lists;         // [groups][2 sets][nq_pad / 32][C][32] raw candidate lists, interleaved per warp
@@ -401,7 +401,7 @@ struct XresParams {
     int       skip_epilogue;   // debug/perf probe: drain nothing (results are garbage)
 };
 
-// TN = rows per tile: 256 for dpad <= 512, 128 for dpad <= 1024 (the resident tile stays <= 128 KB per CTA).
+// TN = rows per tile: 256 for dpad <= 512, 192 for dpad <= 768, 128 for dpad <= 1024 (resident tile <= 144 KB per CTA).
 template <int E, int TN>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -721,7 +721,10 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
     return IVR_OK;
 }
 
-static int xres_tile_rows(const ivr_index* idx) { return idx->dpad <= 512 ? 256 : 128; }
+// rows per resident tile: the largest UMMA N whose half tile (N/2 rows x dpad fp16 per CTA) leaves room for the
+// query ring -- 256 up to 512 dims, 192 up to 768 (N = 128 costs 1.5x the shared-memory operand traffic per
+// FLOP: measured 926 TFLOP/s pipeline-only at 768 dims), 128 up to 1024
+static int xres_tile_rows(const ivr_index* idx) { return idx->dpad <= 512 ? 256 : (idx->dpad <= 768 ? 192 : 128); }
 
 static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int64_t nt, Plan* pl) {
     constexpr int cg = 2;
@@ -785,6 +788,8 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
         int rc;
         if (p.tn == 256) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 256>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
                                         : launch_cluster(search_mma_xres_kernel<0, 256>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        else if (p.tn == 192) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 192>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                             : launch_cluster(search_mma_xres_kernel<0, 192>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         else             rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
                                         : launch_cluster(search_mma_xres_kernel<0, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         IVR_TRY(rc);

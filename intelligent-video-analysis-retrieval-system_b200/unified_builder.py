@@ -82,6 +82,27 @@ class UnifiedBuilderIntegration:
                 })
         return enriched
 
+    def search_unified_fast_batch(self, query_vectors, k: int = 50,
+                                  similarity_threshold: float = 0.0) -> List[List[Dict[str, Any]]]:
+        """``search_unified_fast`` for a batch of queries in one kernel call (same per-query result)."""
+        if not self.unified_index:
+            raise ValueError("Unified index not loaded. Call load_unified_index_fast() first.")
+        batches = self.unified_index.search_vectors_batch(query_vectors, k=k, filter_func=lambda meta: True)
+        out = []
+        for results in batches:
+            enriched = []
+            for result in results:
+                if result["similarity_score"] >= similarity_threshold:
+                    enriched.append({
+                        "metadata": self._convert_metadata_to_legacy(result["metadata"]),
+                        "similarity_score": result["similarity_score"],
+                        "rank": result["rank"],
+                        "temporal_context": self.unified_index.get_temporal_context(result["index"], window_size=3),
+                        "index": result["index"],
+                    })
+            out.append(enriched)
+        return out
+
     def get_thumbnail_fast(self, frame_index: int):
         return self.unified_index.get_thumbnail(frame_index) if self.unified_index else None
 

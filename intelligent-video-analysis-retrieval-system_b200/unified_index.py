@@ -183,6 +183,33 @@ class UnifiedIndex:
                 self.logger.error(f"Search failed: {e}")
             raise
 
+    def search_vectors_batch(self, query_vectors, k: int = 50,
+                             filter_func: Callable = None) -> List[List[Dict[str, Any]]]:
+        """Many queries in ONE kernel call; element i equals ``search_vectors(query_vectors[i], k, filter_func)``.
+
+        The reference is strictly one query per call (unified_index.py:503; system.py:733-826 loops over
+        queries); batching is where the tensor-core path pays off."""
+        if not self.is_loaded:
+            raise ValueError("Index not loaded. Call load_unified_index() first.")
+        q = np.asarray(query_vectors)
+        q = q.reshape(1, -1) if q.ndim == 1 else q.reshape(q.shape[0], -1)
+        distances, indices = self.faiss_index.search(q, k)
+        out = []
+        for drow, irow in zip(distances, indices):
+            results = []
+            for i, (dist, idx) in enumerate(zip(drow, irow)):
+                if idx == -1:
+                    break
+                metadata = self._get_metadata_cached(idx)
+                if metadata is None:
+                    continue
+                if filter_func and not filter_func(metadata):
+                    continue
+                results.append({"rank": i, "similarity_score": float(1.0 - dist),
+                                "metadata": metadata, "index": int(idx)})
+            out.append(results)
+        return out
+
     # README facade (README.md:124-136): batched, raw inner products, metadata join
     def search(self, query, top_k: int = 10):
         """(ids int64[nq,k], scores float32[nq,k] descending inner product, metadata lists)."""

@@ -61,3 +61,13 @@ def search_golden():
              "frame_id": i % 100, "file_hash": f"{i:016x}", "file_size": 1000 + i}
             for i in range(n)]
     return {"xb": arrs["xb"], "xq": arrs["xq"], "meta": meta, "results": js["results"]}
+
+
+@pytest.fixture(scope="session")
+def temporal_golden():
+    """Outputs of the reference's TemporalAnalyzer (tests/golden/make_golden_temporal.py)."""
+    import json
+    arrs = dict(np.load(os.path.join(GOLDEN, "temporal.npz")))
+    with open(os.path.join(GOLDEN, "temporal.json")) as f:
+        cases = json.load(f)
+    return {"arrays": arrs, "cases": cases}

@@ -67,6 +67,36 @@ def test_search_unified_fast_matches_reference(search_golden):
     assert add_unified_index_support(s) is s.unified_builder
 
 
+def test_batched_front_ends_equal_the_per_query_calls(search_golden):
+    """search_vectors_batch / search_unified_fast_batch: one index call for all
+    queries, element i identical to the single-query wrapper the reference golden vectors pin."""
+    sg = search_golden
+    u = make_unified(sg)
+    even = lambda m: m["frame_id"] % 2 == 0      # noqa: E731
+    for k, f in ((20, None), (7, even), (len(sg["xb"]) + 5, None)):
+        batch = u.search_vectors_batch(sg["xq"], k=k, filter_func=f)
+        assert len(batch) == len(sg["xq"])
+        for i, got in enumerate(batch):
+            want = u.search_vectors(sg["xq"][i], k=k, filter_func=f)
+            assert [x["index"] for x in got] == [x["index"] for x in want]
+            assert [x["rank"] for x in got] == [x["rank"] for x in want]
+            np.testing.assert_allclose([x["similarity_score"] for x in got],
+                                       [x["similarity_score"] for x in want], rtol=0, atol=1e-6)
+    assert rows_of(u.search_vectors_batch(sg["xq"][0], k=20)[0])[0][:1] == [0]      # 1-D query -> one result list
+    b = UnifiedBuilderIntegration(system=None)
+    with pytest.raises(ValueError, match="Unified index not loaded"):
+        b.search_unified_fast_batch(sg["xq"])
+    b.unified_index = u
+    for thr in (0.0, 0.3):
+        batch = b.search_unified_fast_batch(sg["xq"], k=30, similarity_threshold=thr)
+        for i, got in enumerate(batch):
+            want = b.search_unified_fast(sg["xq"][i], k=30, similarity_threshold=thr)
+            assert [(x["index"], x["rank"], x["temporal_context"]) for x in got] == \
+                   [(x["index"], x["rank"], x["temporal_context"]) for x in want]
+    with pytest.raises(ValueError, match="Index not loaded"):
+        UnifiedIndex().search_vectors_batch(sg["xq"])
+
+
 def test_facade_tuple(search_golden):
     sg = search_golden
     u = make_unified(sg)

@@ -139,3 +139,42 @@ def test_comparator_flags_real_errors():
     Dbad = D.copy()
     Dbad[1, 3] += 0.01
     assert comparator.compare_topk(Dbad, I, D, I, so)
+
+
+# ---------------------------------------------------------------------------
+# O4: similar-sequence search, pinned to the reference's TemporalAnalyzer
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_sequence_oracle_matches_reference(temporal_golden, name):
+    from oracle import temporal as ot
+    tg = temporal_golden
+    case, db, target = tg["cases"][name], tg["arrays"][f"{name}_db"], tg["arrays"][f"{name}_target"]
+    L, thr = case["sequence_length"], case["threshold"]
+    got = ot.find_similar_sequences(target, db, L, thr)
+    assert [[int(j), float(s)] for j, s in got] == case["hits"]          # bit-for-bit, including the order
+    # the vectorised oracle: same hit set, similarities within float32 rounding of the BLAS/sklearn order
+    sims = ot.window_similarities(target, db, L)
+    want = sorted((j, s) for j, s in case["hits"])
+    t_idx, j_idx = np.nonzero(sims >= np.float32(thr))
+    fast = sorted((int(j), float(sims[t, j])) for t, j in zip(t_idx, j_idx))
+    assert [j for j, _ in fast] == [j for j, _ in want]
+    np.testing.assert_allclose([s for _, s in fast], [s for _, s in want], rtol=0, atol=2e-6)
+    # guard band the GPU test relies on: no window within 1e-4 of the threshold
+    assert not (np.abs(sims - np.float32(thr)) < 1e-4).any()
+    # scene boundaries of the same analyzer (core.py:3584-3642)
+    from oracle import dedup as od
+    assert [list(b) for b in od.detect_scene_boundaries(db, 0.3, 5)] == case["scene_boundaries"]
+
+
+def test_sequence_oracle_short_inputs_and_mean_order(temporal_golden):
+    from oracle import temporal as ot
+    tg = temporal_golden
+    assert tg["cases"]["short"]["hits"] == []
+    assert ot.find_similar_sequences(tg["arrays"]["a_target"][:3], tg["arrays"]["a_db"], 5) == []
+    assert ot.compute_sequence_similarity(np.zeros((3, 4), np.float32), np.zeros((2, 4), np.float32)) == 0.0
+    # the summation order the CUDA kernel implements IS NumPy's float32 np.mean for every length it accepts
+    rng = np.random.default_rng(5)
+    for n in range(1, 129):
+        for _ in range(20):
+            a = (rng.random(n) * 0.3 + 0.7).astype(np.float32)
+            assert np.float32(np.mean([np.float32(v) for v in a])) == ot.numpy_mean_f32(a)

@@ -416,6 +416,34 @@ def test_wrappers_against_reference_golden(search_golden):
     assert ids.shape == (len(sg["xq"]), 5) and np.all(np.diff(scores, axis=1) <= 0)
 
 
+def test_batched_front_end_on_gpu(search_golden):
+    """search_vectors_batch on the CUDA index: every query's hit list against the oracle (the batch runs on a
+    tcgen05 kernel with fp16 queries, the single-query wrapper on the streaming kernel: ties may differ)."""
+    import ivr_b200
+    sg = search_golden
+    u = ivr_b200.UnifiedIndex()
+    u.build_from_embeddings(sg["xb"], sg["meta"])
+    xbn = sg["xb"].copy()
+    flat_ip.normalize_L2(xbn)                          # build_from_embeddings normalises (unified_index.py:1776)
+    ref = flat_ip.IndexFlatIP(xbn.shape[1])
+    ref.add(xbn)
+    k = 25
+    batch = u.search_vectors_batch(sg["xq"], k=k)
+    assert len(batch) == len(sg["xq"])
+    Dr, Ir = ref.search(sg["xq"], k)
+    D = np.array([[1.0 - g["similarity_score"] for g in got] for got in batch], np.float32)
+    I = np.array([[g["index"] for g in got] for got in batch], np.int64)
+    bad = comparator.compare_topk(D, I, Dr, Ir, lambda ids: ref.scores_of(sg["xq"], ids), TOL)
+    assert not bad, bad[:5]
+    for got in batch:
+        assert [g["rank"] for g in got] == list(range(k))
+        assert all(g["metadata"] is sg["meta"][g["index"]] for g in got)
+    b = ivr_b200.UnifiedBuilderIntegration(system=None)
+    b.unified_index = u
+    out = b.search_unified_fast_batch(sg["xq"], k=k, similarity_threshold=0.0)
+    assert [len(o) for o in out] == [sum(g["similarity_score"] >= 0.0 for g in got) for got in batch]
+
+
 def test_faiss_retriever_on_gpu(search_golden):
     import ivr_b200
     sg = search_golden
