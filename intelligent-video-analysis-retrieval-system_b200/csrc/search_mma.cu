@@ -26,9 +26,11 @@
 //     query's admission threshold (register; the max of its own k-th best and a
 //     per-query threshold shared by all CTAs through global memory), a warp vote skips
 //     chunks without survivors, survivors are appended branch-free (predicated stores)
-//     to the query's candidate list; full lists are compacted by a warp bitonic sort.
+//     to the query's candidate list; the 32 interleaved lists of a warp are pruned together, lane-parallel
+//     (warp_prune_lists in mma_common.cuh), when one of them nears its capacity.
 //     The score matrix never reaches shared or global memory.
-// The per-(CTA, query-tile, set) survivors are folded by topk_merge.cu.
+// The raw per-(slot, set, query) lists are folded by topk_merge.cu.  A search runs as a few launches of growing
+// size; each one's exact k-th best scores seed the admission thresholds of the next (search_mma_batch).
 //
 // Algorithmic work: 2 * ntotal * dpad * nq FLOP per search.
 #include "mma_common.cuh"
@@ -626,8 +628,8 @@ __global__ void queries_to_f16_kernel(const float* __restrict__ q, __half* __res
 }
 
 
-// After the prefix phase: every query's shared threshold starts the bulk phase at the EXACT k-th
-// best score of the prefix rows (a valid lower bound of the final k-th best), in the kernel's
+// Between launches: every query's shared threshold starts the next launch at the EXACT k-th
+// best score of the rows searched by the previous one (a valid lower bound of the final k-th best), in the kernel's
 // scaled score domain (keys hold unscaled-by-q_scale scores, i.e. already that domain).
 __global__ void seed_tau_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts,
                                 uint32_t* __restrict__ tau_g, int64_t nq, int k) {
@@ -820,10 +822,10 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
     return IVR_OK;
 }
 
-// One query batch.  Large shards are searched in TWO phases: a prefix of the rows first, whose exact
-// k-th best score per query then seeds the shared admission thresholds of the bulk phase -- the
-// fused top-k epilogue admits ~k/prefix_rows of the scores instead of re-learning its thresholds in
-// every CTA (measured: 22k-45k admissions per query without the seed vs ~2k with it).
+// One query batch.  The shard is searched in several launches of growing size: the exact k-th best score
+// per query of one launch seeds the shared admission thresholds of the next -- the fused top-k epilogue
+// admits ~k * ratio candidates per launch instead of re-learning its thresholds in every list
+// (measured: 22k-45k admissions per query in a single launch).
 static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                             int64_t id_offset, cudaStream_t st, int cg, bool xres, bool first_batch) {
     const int mq = kTileQ * (xres ? 2 : cg);
@@ -906,7 +908,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
 
     // scoring launches are bracketed together by ev[0]/ev[1]; the (tiny) per-phase merges run between
-    // them and are therefore included in "score_ms" when there are two phases
+    // them and are therefore included in "score_ms" when there are several launches
     if (timed) cudaEventRecord(idx->ev[0], st);
     for (int ph = 0; ph < n_phases; ++ph) {
         MergeIn in;
