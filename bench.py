@@ -471,16 +471,27 @@ def run_ours(args):
     res_i = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     q_np = q_host.numpy()
 
+    debug = bool(os.environ.get("IVR_BENCH_DEBUG"))
+
     def e2e_step():
         if world == 1:
             return local.search(q_np, k)                         # C ABI with HOST pointers (H2D + D2H inside)
+        ta = time.perf_counter()
         qd = q_host.to(dev, non_blocking=True)
+        if debug:
+            torch.cuda.synchronize(); tb = time.perf_counter()
         D_, I_ = index.search(qd, k)
+        if debug:
+            torch.cuda.synchronize(); tc = time.perf_counter()
         res_d.copy_(D_, non_blocking=True); res_i.copy_(I_, non_blocking=True)
         torch.cuda.synchronize()
+        if debug and rank == 0:
+            td = time.perf_counter()
+            print(f"[e2e debug] h2d {1e3 * (tb - ta):.2f} ms, search {1e3 * (tc - tb):.2f} ms, d2h {1e3 * (td - tc):.2f} ms",
+                  file=sys.stderr, flush=True)
         return res_d, res_i
 
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
