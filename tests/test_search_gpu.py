@@ -496,3 +496,22 @@ def test_similarity_relationships_vs_oracle():
         for o in wl:                                                # nothing clearly above it is missing
             if s[o] > cut + 1e-3:
                 assert o in gl or o == key, (key, o, s[o], cut)
+
+
+def test_randomised_shapes_auto_path():
+    """Seeded random sweep over (rows, dim, queries, k) through the AUTO path: whichever kernel the
+    dispatcher picks (streaming, small-batch, query-/row-tile-resident) must match the oracle."""
+    rng = np.random.default_rng(2026)
+    seen = set()
+    for case in range(36):
+        n = int(rng.choice([1, 7, 129, 1000, 5000, 20011, 60000]))
+        d = int(rng.choice([1, 3, 64, 65, 100, 128, 257, 384, 512, 513, 768, 1000, 1024]))
+        nq = int(rng.choice([1, 2, 3, 15, 16, 17, 63, 64, 65, 127, 128, 129, 255, 257, 600]))
+        k = int(rng.choice([1, 2, 10, 100, 128, 129, 200]))
+        xb = synth.clip_like(n, d, seed=1000 + case, n_centres=min(64, max(1, n)))
+        xq = synth.clip_like(nq, d, seed=2000 + case, n_centres=min(64, max(1, n)))
+        idx, ref = build(xb)
+        check(idx, ref, xq, k, path=0)
+        seen.add(idx.last_timing()["kernel"])
+        idx.close()
+    assert {"search_stream_kernel", "search_mma_small_kernel", "search_mma_kernel"} <= seen, seen
