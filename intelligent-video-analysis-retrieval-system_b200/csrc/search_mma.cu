@@ -652,9 +652,17 @@ int launch_seed_tau(const uint64_t* keys, const int* counts, uint32_t* tau_g, in
     return IVR_OK;
 }
 
-// IVR_MMA_CTA_GROUP=1 selects the single-CTA variant of the query-tile-resident kernel (default: CTA pairs,
-// cta_group::2); read per call so tests can flip it
-static int cta_group_mode() { return env_int("IVR_MMA_CTA_GROUP", 2) == 1 ? 1 : 2; }
+// IVR_MMA_CTA_GROUP=1 / 2 forces single CTAs / CTA pairs (cta_group::2) for the query-tile-resident kernel;
+// read per call so tests can flip it.
+// Unset / 0: CTA pairs unless single CTAs (128-query tiles) multiply at least 25 % less padding -- measured on the
+// query-tile-resident kernel, 10 M rows: 128 queries 2.01 ms (single CTAs) vs 2.38 ms (pairs), 384: 4.36 vs 4.79,
+// 192 / 256: 2.87 / 3.14 vs 2.52 / 2.71; 100 M x 128 queries: 19.0 vs 25.1 ms.
+static int cta_group_mode(int64_t nq) {
+    const int e = env_int("IVR_MMA_CTA_GROUP", 0);
+    if (e == 1 || e == 2) return e;
+    const int64_t pad1 = (nq + kTileQ - 1) / kTileQ * kTileQ, pad2 = (nq + 2 * kTileQ - 1) / (2 * kTileQ) * (2 * kTileQ);
+    return pad1 * 4 <= pad2 * 3 ? 1 : 2;
+}
 
 bool mma_supported(const ivr_index* idx, int64_t nq, int k) {
     (void)nq;
@@ -948,7 +956,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // Auto: the small-batch (row-streaming) kernel up to IVR_MMA_SMALL_MAX_NQ queries where its shape fits;
     // the row-tile-resident kernel (cta_group::2) from 4 query tiles (> 768 queries) up on large shards.
     const int mode = env_int("IVR_MMA_MODE", 0);
-    const int cg = cta_group_mode();
+    const int cg = cta_group_mode(nq);
     // measured (10 M rows): 512 dims -- 64 queries 2.0 ms small-batch vs 2.1 ms batched, 80: 2.5 vs 2.2, 128: 3.7 vs 2.3
     // (the resident queries squeeze the row ring); 768 dims -- 64..80 queries 2.4-2.6 ms vs 5.7-6.2 ms
     const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", idx->dpad <= kMaxKBlocks * kKBlock ? 64 : 128);
