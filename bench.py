@@ -289,6 +289,28 @@ def run_extras(dev, peaks):
         "frames_per_s": n / ((best[0] + best[1]) * 1e-3), "kept": int(keep.sum().item()), "scenes": int(a.numel()),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                      "algorithmic_bytes_per_launch": n * d * 4}}
+    # CPU path beside it: the line-by-line port of filter.py's scene split + windowed rule (one Python thread by
+    # construction, like the reference) on a bounded slice of the same frames; parity of the slice checked on the way
+    try:
+        from oracle import dedup as od
+        ns = 100_000                                          # a 100 k-frame slice of config B
+        xs = x[:ns].cpu().numpy()
+        cfg = {"enable_similarity_filtering": True, "similarity_threshold": 0.95, "similarity_window_size": w,
+               "use_advanced_similarity_filtering": True, "min_frame_distance": 1}
+        t0 = time.perf_counter()
+        sims = od.calculate_similarities(list(xs))
+        scenes = od.group_into_scenes(od.detect_scene_transitions(sims, 0.75), ns, 2)
+        kept_cpu = od.apply_similarity_filtering_to_scenes(list(xs), list(range(ns)), scenes, cfg)[1]
+        t_cpu = time.perf_counter() - t0
+        from ivr_b200 import frame_filter as ffm
+        kept_gpu = ffm.FrameFilter(window=w, threshold=0.95, transition_threshold=0.75, min_scene_length=2).apply_filters(xs)
+        out["config_b_dedup_1Mx512_w8"]["cpu_baseline"] = {
+            "value": ns / t_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"first {ns} of {n} frames ({t_cpu:.1f} s of CPU work)",
+            "slice_parity": "ok" if list(kept_gpu) == list(kept_cpu) else
+                            f"differs ({len(kept_gpu)} vs {len(kept_cpu)} kept; unguarded synthetic data may sit on a threshold)"}
+    except Exception as e:                                       # informational leg only
+        out["config_b_dedup_1Mx512_w8"]["cpu_baseline"] = {"error": str(e)[:200]}
     return out
 
 
