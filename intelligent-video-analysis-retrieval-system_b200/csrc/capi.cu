@@ -181,8 +181,13 @@ int ivr_index_add(ivr_index* idx, const float* x_host, int64_t n) {
     chunk = std::min(chunk, n);
     IVR_TRY(ensure_pin(idx, 2 * chunk * row_bytes));
     IVR_TRY(ensure_ws(idx, 2 * chunk * row_bytes));
-    cudaEvent_t done[2];
-    for (auto& e : done) IVR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (auto& e : done)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            if (done[0]) cudaEventDestroy(done[0]);
+            set_error("add: cudaEventCreate failed");
+            return IVR_ECUDA;
+        }
     int rc = IVR_OK;
     int64_t off = 0;
     for (int it = 0; off < n; ++it) {
@@ -244,8 +249,6 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
         return IVR_OK;
     }
     int use = path;
-    // measured on B200 (10 M x 512): the streaming kernel wins for 1-2 queries (1.5 ms vs 1.7 ms), the
-    // tcgen05 kernel from 3 queries up (2.1 ms vs 3.8 ms at 4 queries)
     // auto: one query streams on the SIMT kernel; from two queries up the tcgen05 kernels win (measured at
     // 1 M .. 100 M rows, 512 / 768 dims) -- unless only the batched kernels fit the shape, which pay off from three
     if (use == IVR_PATH_AUTO)

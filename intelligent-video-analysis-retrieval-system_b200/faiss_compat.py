@@ -187,8 +187,8 @@ def index_gpu_to_cpu(index):
 
 # -- minimal persistence so reference save/load paths survive --------------
 def serialize_index(index: IndexFlatIP) -> np.ndarray:
-    """Rows are read back from HBM through a search-free path: identity queries are not
-    needed -- the bf16 rows are exported via torch (device memory plumbing)."""
+    """Not provided: index (de)serialisation is the .rvdb container I/O (unified_index.py:1182-1188), which is out of
+    scope; rebuild with ``IndexFlatIP.add`` from the stored embeddings instead."""
     raise NotImplementedError(
         "index (de)serialisation is .rvdb I/O, which is out of scope (SURVEY.md section 8f); "
         "rebuild with IndexFlatIP.add from the stored embeddings instead")
