@@ -867,7 +867,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         // whenever the layouts agree (CTA pairs, one query tile per pair available, 256-row tiles)
         // -- and the launch is short (<= 3 M rows: beyond that re-reading the rows per query tile costs more)
         const bool early_qres = xres && ph + 1 < n_phases && cg == 2 && tq <= idx->sm_count / 2 && tile_rows == kTileN &&
-                                n * tile_rows <= 3000000;
+                                n * tile_rows <= static_cast<int64_t>(env_int("IVR_MMA_EARLY_QRES_MAX_KROWS", 3000)) * 1000;
         IVR_TRY((xres && !early_qres) ? plan_xres(idx, nq, k, t0, n, &plan[ph]) : plan_qres(idx, cg, nq, k, t0, n, &plan[ph]));
     }
     size_t list_bytes = 0, aux_bytes = 0; int max_lists = 2;
