@@ -107,3 +107,79 @@ class ShardedFlatIP:
         dist.all_gather_into_tensor(D_all, D_loc.contiguous(), group=self.group)
         dist.all_gather_into_tensor(I_all, I_loc.contiguous(), group=self.group)
         return self._merge(D_all.view(self.world, nq, k), I_all.view(self.world, nq, k), int(k))
+
+
+# ---------------------------------------------------------------------------
+# Dedup across GPUs: whole videos per rank, no data-path collective
+# ---------------------------------------------------------------------------
+def partition_units(lengths, world_size: int) -> np.ndarray:
+    """Contiguous assignment of indivisible units (videos) to ranks, balanced by frame count:
+    unit u goes to the rank whose ideal frame range contains the unit's midpoint.  Returns unit
+    offsets [world_size + 1]; rank r owns units [off[r], off[r+1])."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    total = int(lengths.sum())
+    off = np.zeros(world_size + 1, dtype=np.int64)
+    if total == 0 or len(lengths) == 0:
+        off[1:] = len(lengths)
+        return off
+    mid = np.cumsum(lengths) - lengths / 2.0
+    owner = np.minimum((mid * world_size / total).astype(np.int64), world_size - 1)
+    for r in range(world_size):
+        off[r + 1] = int(np.searchsorted(owner, r, side="right"))
+    return off
+
+
+class ShardedFrameFilter:
+    """Near-duplicate pruning of many videos on several GPUs: every rank prunes ITS videos (scene split on
+    the consecutive cosine inside each video, then the windowed rule inside each scene -- filter.py:142-315)
+    in two kernel passes over one contiguous frame range; videos are never split, so no halo and no
+    collective on the data path.  ``gather`` (optional, control plane) collects the kept indices.
+
+    ``ops`` is the module providing ``calculate_similarities``, ``detect_scene_transitions``,
+    ``group_into_scenes`` and ``apply_similarity_filtering_to_scenes`` (default: ``frame_filter``, the
+    CUDA path; the world-size-2 gloo test injects the oracle)."""
+
+    def __init__(self, window: int = 8, threshold: float = 0.95, transition_threshold: float = 0.75,
+                 min_scene_length: int = 2, group=None, ops=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.transition_threshold, self.min_scene_length = float(transition_threshold), int(min_scene_length)
+        self.config = {"enable_similarity_filtering": True, "similarity_threshold": float(threshold),
+                       "similarity_window_size": int(window), "use_advanced_similarity_filtering": True,
+                       "min_frame_distance": 1}
+        if ops is None:
+            from . import frame_filter as ops
+        self.ops = ops
+
+    def my_units(self, video_bounds):
+        off = partition_units([e - s + 1 for s, e in video_bounds], self.world)
+        return int(off[self.rank]), int(off[self.rank + 1])
+
+    def filter_videos(self, embeddings, video_bounds) -> list:
+        """Kept GLOBAL frame indices of this rank's videos.  ``video_bounds``: inclusive (start, end) per video,
+        ascending and non-overlapping; ``embeddings`` may be the whole matrix (only this rank's range is read)."""
+        lo, hi = self.my_units(video_bounds)
+        if lo >= hi:
+            return []
+        s0, e1 = video_bounds[lo][0], video_bounds[hi - 1][1]
+        x = embeddings[s0:e1 + 1]
+        sims = self.ops.calculate_similarities(x)                   # one pass over the rank's frames
+        scenes = []
+        for vs, ve in video_bounds[lo:hi]:
+            inside = sims[vs - s0:ve - s0]                          # cosines between frames of THIS video only
+            cuts = self.ops.detect_scene_transitions(inside, self.transition_threshold)
+            for a, b in self.ops.group_into_scenes(cuts, ve - vs + 1, self.min_scene_length):
+                scenes.append((a + vs - s0, b + vs - s0))
+        rows = list(range(s0, e1 + 1))
+        return list(self.ops.apply_similarity_filtering_to_scenes(x, rows, scenes, self.config)[1])
+
+    def gather(self, kept_local: list) -> list:
+        """All ranks' kept indices in video order (control plane: a Python-object all-gather)."""
+        if self.world == 1:
+            return list(kept_local)
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, list(kept_local), group=self.group)
+        return [i for p in parts for i in p]

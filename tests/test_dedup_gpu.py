@@ -155,3 +155,23 @@ def test_config_b_property_1m_frames():
     last = scenes[-2][1] + 1                                     # the last scene may continue past the slice
     assert np.array_equal(keep[:last], want[:last].astype(bool))
     assert st["original"] >= kept.size and st["scenes"] > 1000
+
+
+def test_video_sharded_filter_on_gpu_matches_per_video_rule():
+    """ShardedFrameFilter (world 1, CUDA ops): scenes never cross a video boundary, one kernel pass for all
+    videos of the rank -- identical to pruning every video separately, as the reference does."""
+    from ivr_b200.sharded import ShardedFrameFilter
+    lens = [37, 1, 260, 2, 90, 511]
+    parts = [synth.dedup_frames_guarded(n, 64, window=8, thresholds=(0.95, 0.75), seed=300 + i)[0] for i, n in enumerate(lens)]
+    x = np.concatenate(parts)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    bounds = [(int(s), int(s + n - 1)) for s, n in zip(starts, lens)]
+    got = ShardedFrameFilter(window=8, threshold=0.95).filter_videos(x, bounds)
+    want = []
+    cfg = {"enable_similarity_filtering": True, "similarity_threshold": 0.95, "similarity_window_size": 8,
+           "use_advanced_similarity_filtering": True, "min_frame_distance": 1}
+    for (vs, ve), v in zip(bounds, parts):
+        sims = od.calculate_similarities(list(v))
+        scenes = od.group_into_scenes(od.detect_scene_transitions(sims, 0.75), len(v), 2)
+        want += [vs + i for i in od.apply_similarity_filtering_to_scenes(list(v), list(range(len(v))), scenes, cfg)[1]]
+    assert got == want

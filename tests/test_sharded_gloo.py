@@ -73,3 +73,71 @@ def test_partition_rows():
     assert off[0] == 0 and off[-1] == 100_000_000 and np.all(np.diff(off) == 12_500_000)
     off = partition_rows(10, 4)
     assert off.tolist() == [0, 2, 5, 7, 10]
+
+
+# ---------------------------------------------------------------------------
+# dedup: whole videos per rank, no data-path collective
+# ---------------------------------------------------------------------------
+class _OracleDedupOps:
+    """filter.py's functions from the oracle, with the product module's call signatures."""
+    from oracle import dedup as _od
+    calculate_similarities = staticmethod(lambda x: _OracleDedupOps._od.calculate_similarities(list(x)))
+    detect_scene_transitions = staticmethod(_od.detect_scene_transitions)
+    group_into_scenes = staticmethod(_od.group_into_scenes)
+
+    @staticmethod
+    def apply_similarity_filtering_to_scenes(x, rows, scenes, config):
+        return _OracleDedupOps._od.apply_similarity_filtering_to_scenes(list(x), rows, scenes, config)
+
+
+def _videos(seed=5):
+    rng = np.random.default_rng(seed)
+    lens = [int(v) for v in rng.integers(1, 120, size=9)]
+    x = np.concatenate([synth.dedup_frames(n, 32, seed=100 + i)[0] for i, n in enumerate(lens)])
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    return x, [(int(s), int(s + n - 1)) for s, n in zip(starts, lens)]
+
+
+def _dedup_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ivr_b200.sharded import ShardedFrameFilter
+        x, bounds = _videos()
+        sf = ShardedFrameFilter(window=8, threshold=0.95, ops=_OracleDedupOps)
+        out[rank] = sf.gather(sf.filter_videos(x, bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_dedup_world2_equals_per_video_reference_rule():
+    from oracle import dedup as od
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dedup_worker, args=(2, port, out), nprocs=2, join=True)
+    x, bounds = _videos()
+    cfg = {"enable_similarity_filtering": True, "similarity_threshold": 0.95, "similarity_window_size": 8,
+           "use_advanced_similarity_filtering": True, "min_frame_distance": 1}
+    want = []
+    for vs, ve in bounds:                                           # the reference processes one video at a time
+        v = list(x[vs:ve + 1])
+        scenes = od.group_into_scenes(od.detect_scene_transitions(od.calculate_similarities(v), 0.75), len(v), 2)
+        want += [vs + i for i in od.apply_similarity_filtering_to_scenes(v, list(range(len(v))), scenes, cfg)[1]]
+    assert out[0] == want and out[1] == want and len(want) > 0
+
+
+def test_partition_units_never_splits_and_balances():
+    from ivr_b200.sharded import partition_units
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        lens = rng.integers(1, 1000, size=50)
+        off = partition_units(lens, world)
+        assert off[0] == 0 and off[-1] == 50 and np.all(np.diff(off) >= 0)
+        loads = [int(lens[off[r]:off[r + 1]].sum()) for r in range(world)]
+        assert max(loads) - min(loads) <= 2 * int(lens.max())
+    assert partition_units([], 4).tolist() == [0, 0, 0, 0, 0]
+    assert partition_units([5], 4).tolist()[-1] == 1 and sum(np.diff(partition_units([5], 4))) == 1
