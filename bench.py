@@ -167,7 +167,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"flat inner-product top-{k} over {args.rows}x{dim}, batch {args.nq}",
+           "config": {"workload": f"BASELINE config D: flat inner-product top-{k} over {args.rows}x{dim} "
+                                  f"(fp32 rows on the host), batch {args.nq}",
                       "rows": args.rows, "dim": dim, "nq": args.nq, "k": k,
                       "note": "reference CPU path = oracle port of the faiss.IndexFlatIP contract "
                               "(FAISS is an un-vendored dependency of the reference and is not installed)"},
