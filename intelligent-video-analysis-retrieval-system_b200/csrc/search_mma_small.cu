@@ -19,7 +19,8 @@
 //     each is compared with its query's admission threshold (shared memory, refreshed from the
 //     per-query threshold all CTAs share through global memory); survivors are appended with a warp
 //     ballot to the (CTA, warp, query) candidate list; a list that could overflow on the next tile is
-//     compacted to its k best by a warp bitonic sort, which also raises the thresholds.
+//     compacted to its k best by a warp bitonic sort (registers for k <= 128, in memory above), which
+//     also raises the thresholds.
 // Large shards are searched in up to three launches of growing size (one tile per CTA, then ~380x
 // more, then the rest): the exact k-th best of the rows seen so far seeds the thresholds of the
 // next launch, so that lists almost never need compaction (the cold start of 4 x 148 lists per
@@ -35,8 +36,7 @@ namespace ivr {
 constexpr int kSmallThreads    = 192;                  // producer, MMA issuer, 4 epilogue warps
 constexpr int kSmallTileRows   = 128;                  // rows per tile (UMMA M)
 constexpr int kSmallStageBytes = kSmallTileRows * 128; // one k-block of a row tile: 16 KB
-constexpr int kSmallC          = 256;                  // candidate list capacity (register sort, k <= 128)
-constexpr int kSmallMaxK       = 128;
+constexpr size_t kSmallMaxListBytes = 2ull << 30;      // candidate-list workspace bound (large k x many queries)
 constexpr int kSmallMaxQ       = 128;                  // queries per launch (UMMA N)
 constexpr int kSmallMaxBuf     = 8;                    // TMEM accumulators
 constexpr int kSmallAuxBytes   = 4096;                 // barriers + thresholds + per-warp counts
@@ -45,13 +45,14 @@ struct SmallParams {
     int64_t n_rows;          // rows in this shard
     int     nq, npad;        // real queries; padded to a multiple of 16 (UMMA N)
     int     k;
+    int     C;               // candidate list capacity: 2 * kcap(k) (256 for k <= 128: register sort)
     int     kblocks;         // dpad / 64
     int     stages;          // row ring depth (16 KB each)
     int     nbuf, buf_cols;  // TMEM accumulators and their column stride
     int64_t nt;              // row tiles of this launch
     int64_t tile0;           // first row tile of this launch (row id = (tile0 + j) * 128 + lane)
     uint64_t row_policy;     // L2 eviction priority of the row loads
-    uint64_t* lists;         // [grid][4 warps][npad][kSmallC] raw candidate lists
+    uint64_t* lists;         // [grid][4 warps][npad][C] raw candidate lists
     int*      counts;        // [grid][4 warps][npad]
     uint32_t* tau_g;         // [npad] shared per-query thresholds (order-preserving encoding)
 };
@@ -151,13 +152,15 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int quarter = warp & 3;                              // the TMEM lanes this warp may read
         int* const cnt_w = cnt_s + quarter * kSmallMaxQ;
         const int64_t wslot = static_cast<int64_t>(blockIdx.x) * 4 + quarter;
-        uint64_t* const wl = p.lists + wslot * p.npad * kSmallC;
+        uint64_t* const wl = p.lists + wslot * p.npad * p.C;
         const unsigned lt_mask = (1u << lane) - 1u;
 
         auto compact = [&](int q) {                                // all lanes; list of query q
             const int c = cnt_w[q];
             __syncwarp();
-            const float t = warp_compact_raw<8>(wl + static_cast<int64_t>(q) * kSmallC, c, p.k, kSmallC, lane);
+            uint64_t* const lst = wl + static_cast<int64_t>(q) * p.C;
+            const float t = (p.C == 256) ? warp_compact_raw<8>(lst, c, p.k, p.C, lane)      // register bitonic sort
+                                         : warp_compact_raw<0>(lst, c, p.k, p.C, lane);     // in-memory (k > 128)
             if (lane == 0) {
                 cnt_w[q] = min(c, p.k);
                 if (c >= p.k) {
@@ -173,7 +176,7 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             // make room: one tile adds at most 32 entries (one per lane) to each of this warp's lists
             for (int qb = 0; qb < p.npad; qb += 32) {
                 const int q = qb + lane;
-                unsigned need = __ballot_sync(0xffffffffu, q < p.npad && cnt_w[q] > kSmallC - 32);
+                unsigned need = __ballot_sync(0xffffffffu, q < p.npad && cnt_w[q] > p.C - 32);
                 while (need) { const int l = __ffs(need) - 1; need &= need - 1; compact(qb + l); }
             }
             // fold in the thresholds the other CTAs have published (one warp per tile, round robin)
@@ -225,7 +228,7 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     const int q = c0 + i;
                     const int base = cnt_w[q];
                     if (hit)
-                        wl[static_cast<int64_t>(q) * kSmallC + base + __popc(hits & lt_mask)] =
+                        wl[static_cast<int64_t>(q) * p.C + base + __popc(hits & lt_mask)] =
                             static_cast<uint64_t>(v[i]) | (static_cast<uint64_t>(row) << 32);
                     __syncwarp();
                     if (lane == 0) cnt_w[q] = base + __popc(hits);
@@ -245,16 +248,18 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 }
 
 // ------------------------------------------------------------------ host side ----
-struct SmallShape { int npad, stages, nbuf, buf_cols; size_t smem; };
+struct SmallShape { int npad, stages, nbuf, buf_cols, C; size_t smem; };
 
 static bool small_shape(const ivr_index* idx, int64_t nq, int k, SmallShape* s) {
-    if (k > kSmallMaxK || nq < 1 || nq > kSmallMaxQ) return false;
+    if (k < 1 || k > IVR_MAX_K || nq < 1 || nq > kSmallMaxQ) return false;
     const int npad = static_cast<int>((nq + 15) / 16 * 16);
+    const int C = 2 * kcap_for(k);
+    if (static_cast<size_t>(4 * idx->sm_count) * npad * C * 8 > kSmallMaxListBytes) return false;   // huge k x many queries
     const int64_t q_bytes = static_cast<int64_t>(npad) * idx->dpad * 2;
     if (q_bytes > 128 * 1024) return false;
     const int stages = std::min<int64_t>(12, (kSmemBudget - 1024 - kSmallAuxBytes - q_bytes) / kSmallStageBytes);
     if (stages < 4) return false;
-    s->npad = npad; s->stages = stages;
+    s->npad = npad; s->stages = stages; s->C = C;
     s->buf_cols = std::max(npad, 32);
     s->nbuf = std::min(kSmallMaxBuf, 512 / s->buf_cols);
     s->smem = 1024 + static_cast<size_t>(q_bytes) + static_cast<size_t>(stages) * kSmallStageBytes + kSmallAuxBytes;
@@ -280,7 +285,7 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
     if (env_int("IVR_MMA_TWO_PHASE", 1) && nt >= 4 * static_cast<int64_t>(sms)) {
         const int64_t b0 = sms;
         const int64_t ratio = std::max<int64_t>(2, env_int("IVR_MMA_SMALL_RATIO", 0) > 0 ? env_int("IVR_MMA_SMALL_RATIO", 0)
-                                                                                     : 64ll * 4 * sms / k);
+                                                                                     : static_cast<int64_t>(sh.C / 4) * 4 * sms / k);
         const int64_t b1 = b0 + b0 * ratio;
         bounds[n_phases++] = b0;
         if (nt > b1 + b1 / 2) bounds[n_phases++] = b1;
@@ -294,7 +299,7 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
     const size_t o_q  = carve(static_cast<size_t>(sh.npad) * idx->dpad * 2);
     const size_t o_sc = carve(static_cast<size_t>(sh.npad) * 4);
     const size_t o_tg = carve(static_cast<size_t>(sh.npad) * 4);
-    const size_t o_l  = carve(static_cast<size_t>(max_lists) * sh.npad * kSmallC * 8);
+    const size_t o_l  = carve(static_cast<size_t>(max_lists) * sh.npad * sh.C * 8);
     const size_t o_c  = carve(static_cast<size_t>(max_lists) * sh.npad * 4);
     const size_t o_pk = carve(static_cast<size_t>(3) * nq * k * 8);      // per-launch merged keys [phase][nq][k]
     const size_t o_pc = carve(static_cast<size_t>(3) * nq * 4);
@@ -329,7 +334,7 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
     if (timed) cudaEventRecord(idx->ev[0], st);
     for (int ph = 0; ph < n_phases; ++ph) {
         SmallParams p{};
-        p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.npad = sh.npad; p.k = k;
+        p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.npad = sh.npad; p.k = k; p.C = sh.C;
         p.kblocks = idx->dpad / kKBlock; p.stages = sh.stages; p.nbuf = sh.nbuf; p.buf_cols = sh.buf_cols;
         p.tile0 = bounds[ph]; p.nt = bounds[ph + 1] - bounds[ph];
         p.row_policy = kL2EvictFirst;                                // every row is read exactly once
@@ -342,7 +347,7 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
         idx->launches[0]++;
         MergeIn in{};
         in.entries = p.lists; in.counts = p.counts;
-        in.list_stride = static_cast<int64_t>(sh.npad) * kSmallC; in.q_stride = kSmallC;
+        in.list_stride = static_cast<int64_t>(sh.npad) * sh.C; in.q_stride = sh.C;
         in.cnt_list_stride = sh.npad; in.cnt_q_stride = 1;
         in.n_lists = 4 * grid; in.fixed_count = 0; in.raw = 1;
         if (n_phases == 1) {

@@ -169,7 +169,7 @@ def test_small_kernel_small_indexes(n, small_kernel):
         assert (I[:, n:] == -1).all()
 
 
-@pytest.mark.parametrize("k", [1, 10, 100, 128])
+@pytest.mark.parametrize("k", [1, 10, 100, 128, 129, 300, 1000, 2048])
 def test_small_kernel_k_values(k, small_kernel):
     xb = synth.clip_like(40000, 128, seed=87, n_centres=64)
     xq = synth.clip_like(48, 128, seed=88, n_centres=64)
@@ -179,14 +179,14 @@ def test_small_kernel_k_values(k, small_kernel):
 
 def test_small_kernel_unsupported_shapes_fall_back_in_auto_mode_and_fail_loudly_when_forced(monkeypatch):
     import ivr_b200
-    xb = synth.clip_like(20000, 128, seed=89, n_centres=64)
-    xq = synth.clip_like(8, 128, seed=90, n_centres=64)
+    xb = synth.clip_like(20000, 1024, seed=89, n_centres=64)
+    xq = synth.clip_like(100, 1024, seed=90, n_centres=64)
     idx, ref = build(xb)
-    check(idx, ref, xq, 300, path=2)                              # k > 128: the batched kernel takes it
-    assert idx.last_timing()["kernel"] == "search_mma_kernel"
+    check(idx, ref, xq, 50, path=2)                               # 112 queries x 1024 dims do not fit beside the row ring
+    assert idx.last_timing()["kernel"] == "search_mma_xres_kernel"
     monkeypatch.setenv("IVR_MMA_MODE", "3")
     with pytest.raises(ivr_b200._native.NativeError):
-        idx.search(xq, 300)
+        idx.search(xq, 50)
 
 
 @pytest.mark.parametrize("ratio", [0, 2], ids=["two_launches", "three_launches"])
@@ -219,6 +219,7 @@ def test_small_kernel_rising_scores_force_list_compaction(small_kernel, monkeypa
     idx, ref = build(np.ascontiguousarray(xb, dtype=np.float32))
     check(idx, ref, q, 100, path=2)
     check(idx, ref, q[:1], 128, path=2)
+    check(idx, ref, q[:2], 200, path=2)                           # k > 128: in-memory compaction of 512-entry lists
 
 
 def test_small_kernel_ties_and_duplicates(small_kernel):
