@@ -180,6 +180,14 @@ IVR_API int ivr_sequence_similarity(int device, const float* target_host, int64_
                             int64_t nd, int dim, int seq_len, float threshold, int64_t max_hits,
                             int32_t* hit_t, int64_t* hit_j, float* hit_sim, int64_t* n_hits);
 
+/* eps-neighbourhoods for AdvancedKeyframeExtractor.cluster_similar_frames (filter_research_update.py:113-127:
+ * similarity_matrix = cosine_similarity(embeddings); distance = 1 - similarity; DBSCAN(eps, metric='precomputed')).
+ * e_host: float32 [n, dim] raw rows; adj_host: uint32 [n, (n + 31) / 32]; bit b of word w of row i is set iff
+ * 1 - cos(e_i, e_{32 w + b}) <= eps in float32 (every frame neighbours itself).  The DBSCAN labelling on these
+ * bit rows is sequential and done by the host wrapper.  n <= IVR_MAX_CLUSTER_FRAMES. */
+#define IVR_MAX_CLUSTER_FRAMES 8192
+IVR_API int ivr_cosine_neighbors(int device, const float* e_host, int64_t n, int dim, float eps, uint32_t* adj_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "ivr_sequence_similarity": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                           C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_int64)]),
+    "ivr_cosine_neighbors": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
 }
 
 

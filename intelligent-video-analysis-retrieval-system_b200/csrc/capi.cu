@@ -38,6 +38,8 @@ int sequence_similarity_device(const float* target, int64_t nt, const float* db,
                                unsigned long long* n_hits_dev, float* tn, float* dn, float* cblock,
                                int64_t block_cols, cudaStream_t st);
 int64_t sequence_block_cols(int64_t nt, int64_t nd, int seq_len);
+int cosine_neighbors_device(const float* e, int n, int dim, float eps, float* xn, float* cmat, uint32_t* adj,
+                            cudaStream_t st);
 
 static int require_device(int device) {
     int n = 0;
@@ -535,6 +537,25 @@ int ivr_sequence_similarity(int device, const float* target_host, int64_t nt, co
         IVR_CUDA(cudaMemcpy(hit_j, hj.p, stored * 8, cudaMemcpyDeviceToHost));
         IVR_CUDA(cudaMemcpy(hit_sim, hs.p, stored * 4, cudaMemcpyDeviceToHost));
     }
+    return IVR_OK;
+}
+
+int ivr_cosine_neighbors(int device, const float* e_host, int64_t n, int dim, float eps, uint32_t* adj_host) {
+    if (n < 0 || dim <= 0 || (n > 0 && (!e_host || !adj_host))) { set_error("cosine_neighbors: bad argument"); return IVR_EINVAL; }
+    if (n > IVR_MAX_CLUSTER_FRAMES) {
+        set_error("cosine_neighbors: %lld frames exceed IVR_MAX_CLUSTER_FRAMES=%d", static_cast<long long>(n), IVR_MAX_CLUSTER_FRAMES);
+        return IVR_EUNSUPPORTED;
+    }
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    const size_t words = static_cast<size_t>((n + 31) / 32);
+    DevBuf e, xn, cm, adj;
+    IVR_TRY(e.alloc(static_cast<size_t>(n) * dim * 4)); IVR_TRY(xn.alloc(static_cast<size_t>(n) * dim * 4));
+    IVR_TRY(cm.alloc(static_cast<size_t>(n) * n * 4)); IVR_TRY(adj.alloc(static_cast<size_t>(n) * words * 4));
+    IVR_CUDA(cudaMemcpy(e.p, e_host, static_cast<size_t>(n) * dim * 4, cudaMemcpyHostToDevice));
+    IVR_TRY(cosine_neighbors_device(static_cast<float*>(e.p), static_cast<int>(n), dim, eps, static_cast<float*>(xn.p),
+                                    static_cast<float*>(cm.p), static_cast<uint32_t*>(adj.p), nullptr));
+    IVR_CUDA(cudaMemcpy(adj_host, adj.p, static_cast<size_t>(n) * words * 4, cudaMemcpyDeviceToHost));
     return IVR_OK;
 }
 

@@ -17,6 +17,10 @@
 //                             interleaved accumulators up to 128), threshold, atomic append of the hit.
 // The database is processed in chunks so that the cosine block stays below kMaxBlockBytes.
 // Algorithmic work: 2 * nt * nd * d FLOP.
+//
+// The same normalise + cosine-matrix kernels give the eps-neighbourhoods of the DBSCAN phase of
+// filter_research_update.py (cluster_similar_frames, 113-134): seq_adjacency_kernel packs
+// `1 - cos <= eps` into one bit per frame pair; the labelling itself is sequential and runs on the host.
 #include "common.cuh"
 
 #include <algorithm>
@@ -152,5 +156,32 @@ int64_t sequence_block_cols(int64_t nt, int64_t nd, int seq_len) {
 }
 
 int sequence_max_len() { return kSeqMaxLen; }
+
+// ---- eps-neighbourhoods for the DBSCAN phase (filter_research_update.py:113-127) --------------------
+// adj[i][w] bit b  <=>  1 - cos(e_i, e_{32 w + b}) <= eps   (float32, as NumPy evaluates `1 - sim <= eps`)
+__global__ void seq_adjacency_kernel(const float* __restrict__ C, int n, float eps, uint32_t* __restrict__ adj, int words) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;   // one warp per (row, word)
+    if (wid >= static_cast<int64_t>(n) * words) return;
+    const int i = static_cast<int>(wid / words), w = static_cast<int>(wid % words);
+    const int j = w * 32 + lane;
+    const bool in = j < n && __fsub_rn(1.0f, C[static_cast<int64_t>(i) * n + j]) <= eps;
+    const unsigned bits = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) adj[static_cast<int64_t>(i) * words + w] = bits;
+}
+
+// e: device float32 [n, d]; xn: [n, d] scratch; cmat: [n, n] scratch; adj: [n, words] out
+int cosine_neighbors_device(const float* e, int n, int dim, float eps, float* xn, float* cmat, uint32_t* adj,
+                            cudaStream_t st) {
+    const int words = (n + 31) / 32;
+    const int64_t threads = static_cast<int64_t>(n) * 32;
+    seq_normalize_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(e, xn, n, dim);
+    dim3 g1(static_cast<unsigned>((n + 63) / 64), static_cast<unsigned>((n + 63) / 64));
+    seq_cosine_kernel<<<g1, 256, 0, st>>>(xn, xn, cmat, n, n, dim, n);
+    const int64_t t2 = static_cast<int64_t>(n) * words * 32;
+    seq_adjacency_kernel<<<static_cast<unsigned>((t2 + 255) / 256), 256, 0, st>>>(cmat, n, eps, adj, words);
+    IVR_CUDA(cudaGetLastError());
+    return IVR_OK;
+}
 
 }  // namespace ivr

@@ -12,6 +12,7 @@ CLIP outputs to sklearn, which keeps the dtype).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -224,6 +225,52 @@ def temporal_window_filter(embeddings, threshold: float = 0.95, temporal_window:
 # ---------------------------------------------------------------------------
 # README facade
 # ---------------------------------------------------------------------------
+def cluster_similar_frames(embeddings, frame_indices=None, eps: float = 0.05, min_samples: int = 2,
+                           device=None) -> List[List[int]]:
+    """filter_research_update.py:113-134 (Phase 2): DBSCAN on ``1 - cosine_similarity`` inside a scene.
+
+    The n x n cosine matrix and the eps-neighbourhood bits come from the GPU (``ivr_cosine_neighbors``); the
+    labelling is scikit-learn's published ``dbscan_inner`` rule on those bits (index-order scan, depth-first
+    growth through core samples, border points to the first cluster that reaches them, noise = -1) and the
+    groups are returned like the reference's ``defaultdict`` -- label first-seen order, the noise label
+    forming one group like any other.  ``frame_indices`` is accepted and unused, as in the reference.
+
+    Divergence kept on purpose: with recent scikit-learn the reference RAISES ("Negative values in data")
+    whenever float rounding makes some 1 - cos(e_i, e_i) slightly negative; here such distances simply count
+    as <= eps (what the rule means)."""
+    n = len(embeddings)
+    if n < 2:
+        return [[0]] if n else []
+    x, _ = _as_matrix(embeddings)
+    words = (n + 31) // 32
+    adj = np.empty((n, words), np.uint32)
+    nat.check(nat.lib.ivr_cosine_neighbors(nat.default_device() if device is None else int(device),
+                                           x.ctypes.data, n, x.shape[1], C.c_float(eps), adj.ctypes.data))
+    bits = np.unpackbits(adj.view(np.uint8), axis=1, bitorder="little")[:, :n].astype(bool)
+    neighborhoods = [np.nonzero(row)[0] for row in bits]
+    is_core = [len(nb) >= min_samples for nb in neighborhoods]
+    labels = [-1] * n
+    label_num, stack = 0, []
+    for i in range(n):                                     # sklearn/cluster/_dbscan_inner.pyx
+        if labels[i] != -1 or not is_core[i]:
+            continue
+        while True:
+            if labels[i] == -1:
+                labels[i] = label_num
+                if is_core[i]:
+                    for v in neighborhoods[i]:
+                        if labels[v] == -1:
+                            stack.append(int(v))
+            if not stack:
+                break
+            i = stack.pop()
+        label_num += 1
+    clusters: Dict[int, List[int]] = {}
+    for idx, label in enumerate(labels):
+        clusters.setdefault(label, []).append(idx)
+    return list(clusters.values())
+
+
 class FrameFilter:
     """``FrameFilter().apply_filters(embeddings, window=8, threshold=0.95) -> kept indices``
     (README.md:192-196): scene split on the consecutive cosine, then the windowed

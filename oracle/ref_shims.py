@@ -14,6 +14,8 @@ What is shimmed and why:
                          ``faiss_compat``) is injected.
   * ``h5py``, ``lz4``, ``lz4.frame`` -- unified_index.py:29-30; empty stubs
                          (only the .rvdb I/O uses them, which is out of scope).
+  * ``imagehash``, ``colorama`` -- filter_research_update.py:15,17; absent; stubs
+                         (perceptual hashing of image files and coloured logging only).
   * CWD               -- ``utils.Config()`` creates exports/ index/ logs/
                          metadata/ relative to the CWD (utils.py:267-268), so the
                          import happens inside a temp dir.
@@ -54,6 +56,19 @@ def _stub_transformers():
     return tr
 
 
+def _stub_colorama():
+    """colorama is only used for coloured log lines (filter_research_update.py:17-35)."""
+    co = types.ModuleType("colorama")
+
+    class _Codes:
+        def __getattr__(self, _):
+            return ""
+
+    co.Fore, co.Back, co.Style = _Codes(), _Codes(), _Codes()
+    co.init = lambda *a, **k: None
+    return co
+
+
 def oracle_faiss_module():
     """A ``faiss``-shaped module backed by oracle.flat_ip (for pinning the wrappers)."""
     from . import flat_ip
@@ -74,14 +89,17 @@ def reference_modules(faiss_module=None, names=("filter",)):
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_DIR}")
     saved = {k: sys.modules.get(k) for k in
-             ("transformers", "faiss", "h5py", "lz4", "lz4.frame",
-              "filter", "core", "utils", "unified_index", "unified_builder")}
+             ("transformers", "faiss", "h5py", "lz4", "lz4.frame", "imagehash", "colorama",
+              "filter", "filter_research_update", "core", "utils", "unified_index", "unified_builder")}
     old_path = list(sys.path)
     old_cwd = os.getcwd()
     tmp = tempfile.mkdtemp(prefix="ivr_ref_")
     try:
-        if "filter" in names:
+        if "filter" in names or "filter_research_update" in names:
             sys.modules["transformers"] = _stub_transformers()
+        if "filter_research_update" in names:       # filter_research_update.py:15,17 -- absent, presentation only
+            sys.modules["imagehash"] = types.ModuleType("imagehash")
+            sys.modules["colorama"] = _stub_colorama()
         sys.modules["faiss"] = faiss_module or oracle_faiss_module()
         for stub in ("h5py", "lz4", "lz4.frame"):
             mod = types.ModuleType(stub)
@@ -89,7 +107,7 @@ def reference_modules(faiss_module=None, names=("filter",)):
                 mod.File = object
             sys.modules[stub] = mod
         sys.modules["lz4"].frame = sys.modules["lz4.frame"]
-        for k in ("filter", "core", "utils", "unified_index", "unified_builder"):
+        for k in ("filter", "filter_research_update", "core", "utils", "unified_index", "unified_builder"):
             sys.modules.pop(k, None)
         sys.path.insert(0, REFERENCE_DIR)
         os.chdir(tmp)

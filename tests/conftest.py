@@ -71,3 +71,13 @@ def temporal_golden():
     with open(os.path.join(GOLDEN, "temporal.json")) as f:
         cases = json.load(f)
     return {"arrays": arrs, "cases": cases}
+
+
+@pytest.fixture(scope="session")
+def research_golden():
+    """Outputs of the reference's AdvancedKeyframeExtractor (tests/golden/make_golden_research.py)."""
+    import json
+    arrs = dict(np.load(os.path.join(GOLDEN, "research.npz")))
+    with open(os.path.join(GOLDEN, "research.json")) as f:
+        cases = json.load(f)
+    return {"arrays": arrs, "cases": cases}

@@ -175,3 +175,39 @@ def test_video_sharded_filter_on_gpu_matches_per_video_rule():
         scenes = od.group_into_scenes(od.detect_scene_transitions(sims, 0.75), len(v), 2)
         want += [vs + i for i in od.apply_similarity_filtering_to_scenes(list(v), list(range(len(v))), scenes, cfg)[1]]
     assert got == want
+
+
+# ---------------------------------------------------------------------------
+# DBSCAN phase of filter_research_update.py (113-134): GPU eps-neighbourhoods + host labelling
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["s384", "s64", "s512"])
+def test_cluster_similar_frames_matches_reference_golden(research_golden, name):
+    from ivr_b200 import frame_filter as ff
+    from oracle import cluster as oc
+    case, x = research_golden["cases"][name], research_golden["arrays"][name]
+    assert ff.detect_scene_changes(list(x), case["scene_threshold"]) == case["scene_changes"]
+    for span, want in case["clusters"].items():
+        a, b = (int(v) for v in span.split(":"))
+        got = ff.cluster_similar_frames(list(x[a:b]), list(range(b - a)), eps=case["eps"], min_samples=case["min_samples"])
+        if want == "ValueError":     # the reference raised on rounding noise; the rule itself is the oracle's
+            want = oc.cluster_similar_frames(list(x[a:b]), case["eps"], case["min_samples"])
+        assert got == want, span
+
+
+def test_cluster_similar_frames_large_scene_vs_oracle():
+    from ivr_b200 import _native as nat, frame_filter as ff
+    from oracle import cluster as oc
+    rng = np.random.default_rng(77)
+    base = rng.standard_normal((40, 384)).astype(np.float32)
+    x = (base[rng.integers(0, 40, 2500)] + np.float32(0.12) * rng.standard_normal((2500, 384)).astype(np.float32)).astype(np.float32)
+    sim = oc.cosine_matrix(x)
+    eps = 0.05
+    while (np.abs((1 - sim) - np.float32(eps)) < 1e-5)[~np.eye(len(x), dtype=bool)].any():
+        eps += 3e-5                                   # guard band around eps
+    want = oc.cluster_similar_frames(list(x), eps, 3)
+    got = ff.cluster_similar_frames(x, eps=eps, min_samples=3)
+    assert got == want and 1 < len(got) < len(x)
+    assert ff.cluster_similar_frames([]) == [] and ff.cluster_similar_frames([x[0]]) == [[0]]
+    assert ff.cluster_similar_frames([x[0], x[0]]) == [[0, 1]]
+    with pytest.raises(nat.NativeError):
+        ff.cluster_similar_frames(np.zeros((8193, 4), np.float32))

@@ -178,3 +178,35 @@ def test_sequence_oracle_short_inputs_and_mean_order(temporal_golden):
         for _ in range(20):
             a = (rng.random(n) * 0.3 + 0.7).astype(np.float32)
             assert np.float32(np.mean([np.float32(v) for v in a])) == ot.numpy_mean_f32(a)
+
+
+# ---------------------------------------------------------------------------
+# O5: DBSCAN phase + scene changes of filter_research_update.py, pinned to the reference (real scikit-learn)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["s384", "s64", "s512"])
+def test_cluster_oracle_matches_reference(research_golden, name):
+    from oracle import cluster as oc, dedup as od
+    rg = research_golden
+    case, x = rg["cases"][name], rg["arrays"][name]
+    assert od.detect_scene_changes(list(x), case["scene_threshold"]) == case["scene_changes"]
+    pinned = 0
+    for span, want in case["clusters"].items():
+        a, b = (int(v) for v in span.split(":"))
+        got = oc.cluster_similar_frames(list(x[a:b]), case["eps"], case["min_samples"])
+        if want == "ValueError":                  # reference + recent scikit-learn: negative 1 - cos from rounding
+            assert (1 - oc.cosine_matrix(x[a:b])).min() < 0
+            continue
+        assert got == want, span
+        pinned += 1
+    assert pinned >= 5
+
+
+def test_cluster_oracle_edges_and_dbscan_rule(research_golden):
+    from oracle import cluster as oc
+    assert research_golden["cases"]["edge"] == {"empty": [], "one": [[0]]}
+    assert oc.cluster_similar_frames([]) == [] and oc.cluster_similar_frames([np.ones(4, np.float32)]) == [[0]]
+    # chain 0-1-2 (core 1), border 3 reached from core 2?, isolated 4: labels follow the index-order / LIFO rule
+    nb = [np.array([0, 1]), np.array([0, 1, 2]), np.array([1, 2, 3]), np.array([2, 3]), np.array([4])]
+    assert oc.dbscan_labels(nb, 2).tolist() == [0, 0, 0, 0, -1]
+    assert oc.dbscan_labels(nb, 3).tolist() == [0, 0, 0, 0, -1]      # 0 and 3 are border points of cores 1 and 2
+    assert oc.groups_from_labels([1, -1, 1, 0]) == [[0, 2], [1], [3]]
