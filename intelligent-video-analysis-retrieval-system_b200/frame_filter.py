@@ -271,6 +271,31 @@ def cluster_similar_frames(embeddings, frame_indices=None, eps: float = 0.05, mi
     return list(clusters.values())
 
 
+def select_representative_frame(cluster_indices, embeddings, frame_info=None) -> int:
+    """filter_research_update.py:136-155 (Phase 3): the cluster member closest (cosine) to the cluster's mean
+    embedding; first maximum wins.  O(members x d) host arithmetic in the input dtype, in sklearn's order
+    (normalise, then dot) -- glue between the GPU clustering and the caller, like the scene bookkeeping."""
+    if len(cluster_indices) == 1:
+        return cluster_indices[0]
+    members = np.stack([np.asarray(embeddings[i]) for i in cluster_indices])
+    centroid = np.mean(members, axis=0)
+
+    def _unit(v):
+        v = np.array(v, copy=True)
+        if v.dtype not in (np.float32, np.float64):
+            v = v.astype(np.float64)
+        nrm = np.sqrt(np.einsum("ij,ij->i", v, v))
+        nrm[nrm == 0.0] = 1.0
+        return v / nrm[:, np.newaxis]
+
+    best_idx, best_sim = 0, -1
+    for i in range(len(cluster_indices)):
+        sim = (_unit(members[i:i + 1]) @ _unit(centroid[None, :]).T)[0][0]
+        if sim > best_sim:
+            best_sim, best_idx = sim, i
+    return cluster_indices[best_idx]
+
+
 class FrameFilter:
     """``FrameFilter().apply_filters(embeddings, window=8, threshold=0.95) -> kept indices``
     (README.md:192-196): scene split on the consecutive cosine, then the windowed

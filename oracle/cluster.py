@@ -71,3 +71,18 @@ def cluster_similar_frames(embeddings, eps: float = 0.05, min_samples: int = 2) 
     radius = dist.dtype.type(eps)                       # NumPy weak-scalar promotion: compared in dist's dtype
     neighborhoods = [np.nonzero(row <= radius)[0] for row in dist]
     return groups_from_labels(dbscan_labels(neighborhoods, min_samples))
+
+
+def select_representative_frame(cluster_indices, embeddings):
+    """filter_research_update.py:136-155 -- the member closest (cosine) to the cluster's mean embedding; first
+    maximum wins; a single-member cluster returns that member."""
+    from .dedup import cos1
+    if len(cluster_indices) == 1:
+        return cluster_indices[0]
+    centroid = np.mean([embeddings[i] for i in cluster_indices], axis=0)
+    best_idx, best_sim = 0, -1
+    for i, emb_idx in enumerate(cluster_indices):
+        sim = cos1(embeddings[emb_idx], centroid)
+        if sim > best_sim:
+            best_sim, best_idx = sim, i
+    return cluster_indices[best_idx]

@@ -1,5 +1,5 @@
-"""Golden vectors for filter_research_update.AdvancedKeyframeExtractor.detect_scene_changes (101-111) and
-.cluster_similar_frames (113-134), produced by running the UNMODIFIED reference with real scikit-learn.
+"""Golden vectors for filter_research_update.AdvancedKeyframeExtractor.detect_scene_changes (101-111),
+.cluster_similar_frames (113-134) and .select_representative_frame (136-155), produced by running the UNMODIFIED reference with real scikit-learn.
 
     python tests/golden/make_golden_research.py        (needs /root/reference; writes research.npz/.json)
 
@@ -70,8 +70,15 @@ def main():
                     assert "Negative values" in str(e)
                     clusters[f"{a}:{b}"] = "ValueError"
                     raised += 1
+            # Phase 3 (select_representative_frame, 136-155) on every group the reference produced
+            reps = {}
+            for span, groups in clusters.items():
+                if groups == "ValueError":
+                    continue
+                a, b = (int(v) for v in span.split(":"))
+                reps[span] = [int(ex.select_representative_frame(g, emb[a:b], None)) for g in groups]
             arrays[name] = x
-            cases[name] = {"scene_changes": [int(c) for c in changes], "clusters": clusters,
+            cases[name] = {"scene_changes": [int(c) for c in changes], "clusters": clusters, "representatives": reps,
                            "eps": fr.CLUSTER_EPS, "min_samples": fr.MIN_CLUSTER_SIZE, "scene_threshold": fr.SCENE_THRESHOLD}
             ok = [v for v in clusters.values() if v != "ValueError"]
             print(name, "scenes", len(changes) - 1, "slices", len(clusters), "raised", raised,

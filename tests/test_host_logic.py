@@ -157,3 +157,18 @@ def test_scene_bookkeeping_matches_reference(dedup_golden):
     cfg = ff.create_config()
     assert cfg["similarity_threshold"] == 0.95 and cfg["similarity_window_size"] == 5
     assert UnifiedIndexConfig().thumbnail_size == (224, 224)
+
+
+def test_select_representative_frame_matches_reference(research_golden):
+    """Phase 3 of filter_research_update.py (136-155) on every cluster the reference produced."""
+    n = 0
+    for name in ("s384", "s64", "s512"):
+        case, x = research_golden["cases"][name], research_golden["arrays"][name]
+        for span, groups in case["clusters"].items():
+            if groups == "ValueError":
+                continue
+            a, b = (int(v) for v in span.split(":"))
+            emb = list(x[a:b])
+            assert [ff.select_representative_frame(g, emb, None) for g in groups] == case["representatives"][span]
+            n += sum(len(g) > 1 for g in groups)
+    assert n >= 20

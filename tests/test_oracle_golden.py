@@ -197,6 +197,7 @@ def test_cluster_oracle_matches_reference(research_golden, name):
             assert (1 - oc.cosine_matrix(x[a:b])).min() < 0
             continue
         assert got == want, span
+        assert [oc.select_representative_frame(g, list(x[a:b])) for g in got] == case["representatives"][span], span
         pinned += 1
     assert pinned >= 5
 
