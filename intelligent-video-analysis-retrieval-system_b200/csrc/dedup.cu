@@ -265,6 +265,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2): two IEEE fp32 operations per issued instruction.  The register-window
+// kernel is bound by instruction issue (ncu: 69 % issue-active, 144 of ~230 instructions per frame are FMAs), not
+// by the FP32 pipe or HBM, so halving the FMA instruction count is what moves it.
+__device__ __forceinline__ void ffma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(c0), "=f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 template <int DV>
 __global__ void __launch_bounds__(kRwWarps * 32, 3)
 banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
@@ -309,23 +323,24 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
                 // The 8 dot products are taken with the RAW row and scaled by 1/||row|| afterwards
                 // (dot(x/|x|, w) == dot(x, w)/|x| up to one rounding), so the norm reduction and the
                 // dot reduction are two independent shuffle chains instead of one long one.
-                float ss = 0.f;
+                float ss0 = 0.f, ss1 = 0.f;                                 // even / odd partial sums (FFMA2)
 #pragma unroll
                 for (int j = 0; j < DV; ++j) {
-                    ss = fmaf(cur[j].x, cur[j].x, ss); ss = fmaf(cur[j].y, cur[j].y, ss);
-                    ss = fmaf(cur[j].z, cur[j].z, ss); ss = fmaf(cur[j].w, cur[j].w, ss);
+                    ffma2(ss0, ss1, cur[j].x, cur[j].y, cur[j].x, cur[j].y);
+                    ffma2(ss0, ss1, cur[j].z, cur[j].w, cur[j].z, cur[j].w);
                 }
+                float ss = ss0 + ss1;
                 float acc[kRwWindow];
 #pragma unroll
                 for (int dd = 1; dd <= kRwWindow; ++dd) {
                     const int w = (u - dd + 2 * kRwWindow) % kRwWindow;     // slot of frame ii - dd
-                    float a = 0.f;
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int j = 0; j < DV; ++j) {
-                        a = fmaf(cur[j].x, win[w][j].x, a); a = fmaf(cur[j].y, win[w][j].y, a);
-                        a = fmaf(cur[j].z, win[w][j].z, a); a = fmaf(cur[j].w, win[w][j].w, a);
+                        ffma2(a0, a1, cur[j].x, cur[j].y, win[w][j].x, win[w][j].y);
+                        ffma2(a0, a1, cur[j].z, cur[j].w, win[w][j].z, win[w][j].w);
                     }
-                    acc[dd - 1] = a;
+                    acc[dd - 1] = a0 + a1;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -349,8 +364,8 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
                 val *= inv;
 #pragma unroll
                 for (int j = 0; j < DV; ++j) {                              // frame ii (normalised) replaces frame ii - 8
-                    win[u][j].x = cur[j].x * inv; win[u][j].y = cur[j].y * inv;
-                    win[u][j].z = cur[j].z * inv; win[u][j].w = cur[j].w * inv;
+                    fmul2(win[u][j].x, win[u][j].y, cur[j].x, cur[j].y, inv, inv);
+                    fmul2(win[u][j].z, win[u][j].w, cur[j].z, cur[j].w, inv, inv);
                 }
                 const int dd = (lane >> 2) + 1;
                 const bool ge = dd <= window && ii - dd >= 0 && val >= thr;
