@@ -234,12 +234,11 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (nload > 0) mbar_wait(q_empty, (nload - 1) & 1);
     } else if (warp == 1 && lane == 0) {
         // ============================ MMA issuer (leader CTA) =================
-        // q_empty ("the MMAs reading the query tile have retired") is committed at the end of a visit
-        // when the next visit needs another query tile and at the very last visit.  The
-        // producer consumes all completions but the last; this thread (in both CTAs of a pair) waits
-        // for the last one so that no asynchronous arrive can land after the CTA has retired.
+        // q_empty ("the MMAs reading the query tile have retired") is committed at the end of every visit;
+        // the producer consumes the completions in order and waits for the last one before it retires, so
+        // no asynchronous arrive can land after the CTA has gone.
         constexpr uint32_t idesc = make_idesc(kTileQ * CG, kTileN);
-        int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0;
+        int stage = 0; uint32_t phase = 0; int nload = 0;
         for_each_unit(p, group,
             [&](int, int, bool reload, int) {
                 if (!reload) return;
@@ -268,12 +267,8 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 umma_commit<CG>(tfull_bar(acc));                       // accumulator ready for its epilogue set
             },
             [&](int, int, int, bool release_q) {
-                if (release_q) {
-                    if (cta_rank == 0) umma_commit<CG>(q_empty);
-                    ++ncommit;
-                }
+                if (release_q && cta_rank == 0) umma_commit<CG>(q_empty);
             });
-        (void)ncommit;
     } else if (warp >= 4) {
         // ============================ epilogue: fused top-k ====================
         const int set = (warp - 4) >> 2;                           // accumulator / list set 0 or 1
@@ -486,7 +481,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     } else if (warp == 1 && lane == 0) {
         // ============================ MMA issuer (leader CTA) =================
         constexpr uint32_t idesc = make_idesc(kTileQ * CG, TN);
-        int stage = 0; uint32_t phase = 0; int nload = 0; int ncommit = 0; int64_t n = 0;
+        int stage = 0; uint32_t phase = 0; int nload = 0; int64_t n = 0;
         for (int64_t j = j0; j < j1; ++j) {
             if (cta_rank == 0) mbar_wait(x_full, nload & 1);
             ++nload;
@@ -513,9 +508,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 }
                 umma_commit<CG>(x_empty);                           // row tile released when its MMAs retire
             }
-            ++ncommit;
         }
-        (void)ncommit;
     } else if (warp >= 4) {
         // ============================ epilogue: fused top-k ====================
         const int set = (warp - 4) >> 2;
