@@ -287,11 +287,15 @@ __device__ __forceinline__ unsigned warp_prune_lists(uint64_t* my_list, int& cnt
     int c[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) c[j] = 0;
-#pragma unroll 4
-    for (int i = 0; i < cmax; ++i) {
-        const float v = (act && i < cnt) ? raw_score(my_list[static_cast<int64_t>(i) * kListStride]) : NEG_INF;
+    for (int i0 = 0; i0 < cmax; i0 += 8) {                       // 8 independent loads in flight per round
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] += (v > s[j]) ? 1 : 0;
+        for (int u = 0; u < 8; ++u)
+            v[u] = (act && i0 + u < cnt) ? raw_score(my_list[static_cast<int64_t>(i0 + u) * kListStride]) : NEG_INF;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] += (v[u] > s[j]) ? 1 : 0;
     }
     float pv = NEG_INF; bool ok = false;
 #pragma unroll
