@@ -965,7 +965,11 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // per launch: row-tile-resident is bounded by its candidate-list workspace, query-tile-resident by
     // one query tile per CTA group
     idx->last_kernel = xres ? "search_mma_xres_kernel" : "search_mma_kernel";
-    const int64_t per_launch = xres ? 16384 : static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
+    int64_t per_launch = static_cast<int64_t>(idx->sm_count / cg) * kTileQ * cg;
+    if (xres) {                                                    // one list per (pair, set, query): keep them under 8 GiB
+        const int64_t per_query = static_cast<int64_t>(idx->sm_count / 2) * 2 * (2 * kcap_for(k)) * 8;
+        per_launch = std::min<int64_t>(16384, std::max<int64_t>(2 * kTileQ, ((8ll << 30) / per_query) / (2 * kTileQ) * (2 * kTileQ)));
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
         const int64_t b = std::min(per_launch, nq - q0);
         IVR_TRY(search_mma_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k, id_offset, st,

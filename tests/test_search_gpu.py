@@ -571,3 +571,14 @@ def test_full_size_configs_against_exact_scan(n, d, nqs):
                     assert s_k - TOL <= d_ <= s_k + 2 * TOL, (nq, q, i_, d_, s_k)     # only near-k ties may differ
             assert np.all(np.diff(Dn[q]) <= 0) and len(set(In[q].tolist())) == k
     idx.close()
+
+
+def test_row_tile_resident_large_k_runs_in_several_query_batches(monkeypatch):
+    """k = 2048 makes every candidate list 4096 entries: the row-tile-resident kernel then takes at most 1536
+    queries per launch (8 GiB list budget), so 1700 queries run as two batches."""
+    monkeypatch.setenv("IVR_MMA_MODE", "2")
+    xb = synth.clip_like(6000, 64, seed=111, n_centres=32)
+    xq = synth.clip_like(1700, 64, seed=112, n_centres=32)
+    idx, ref = build(xb)
+    check(idx, ref, xq, 2048, path=2)
+    assert idx.last_timing()["kernel"] == "search_mma_xres_kernel"
