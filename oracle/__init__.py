@@ -11,10 +11,15 @@ flat_ip     NumPy restatement of the ``faiss.IndexFlatIP`` contract the
             reference calls (unified_index.py:503, 1767-1779; core.py:891).
 dedup       NumPy restatement of the reference's cosine dedup rules
             (filter.py:142-315, video_frame_filter.py:63-70, core.py:3612-3630).
+temporal    ``TemporalAnalyzer.find_similar_sequences`` / ``_compute_sequence_similarity``
+            (core.py:3644-3702, 3812-3832).
+cluster     The DBSCAN phase and representative selection of
+            filter_research_update.py (113-155), with scikit-learn's published
+            ``dbscan_inner`` rule restated.
 comparator  The tie-aware top-k comparator.
 synth       Seeded synthetic generators for the BASELINE.json configs.
 ref_shims   Import shims that let the *reference's own files* run in the
-            authoring container (used by tests/golden/make_golden.py only;
+            authoring container (used by the tests/golden/make_golden*.py scripts only;
             /root/reference does not exist on the GPU box).
 
 Pinning status
@@ -22,6 +27,11 @@ Pinning status
 * dedup:   PINNED -- checked bit-for-bit against the reference's own
            ``filter.py`` functions (golden fixtures in tests/golden/ were
            produced by importing the reference here).
+* temporal, cluster: PINNED -- bit-for-bit against the reference's own
+           ``TemporalAnalyzer`` / ``AdvancedKeyframeExtractor`` methods (real
+           scikit-learn), fixtures tests/golden/temporal.*, research.*.
+           The FIFO rule of filter_research_update.py:316-338 is inline code of
+           ``process_video`` and stays restated only.
 * wrappers (``search_vectors``, ``search_unified_fast``,
            ``FAISSRetriever.search``): PINNED -- fixtures produced by running
            the reference's own classes on top of ``flat_ip`` through a
