@@ -81,3 +81,13 @@ def research_golden():
     with open(os.path.join(GOLDEN, "research.json")) as f:
         cases = json.load(f)
     return {"arrays": arrs, "cases": cases}
+
+
+@pytest.fixture(scope="session")
+def relationships_golden():
+    """Output of the reference's MetadataManager._build_similarity_relationships (make_golden_relationships.py)."""
+    import json
+    feats = dict(np.load(os.path.join(GOLDEN, "relationships.npz")))
+    with open(os.path.join(GOLDEN, "relationships.json")) as f:
+        graph = json.load(f)["graph"]
+    return {"features": feats, "graph": graph}

@@ -211,3 +211,15 @@ def test_cluster_oracle_edges_and_dbscan_rule(research_golden):
     assert oc.dbscan_labels(nb, 2).tolist() == [0, 0, 0, 0, -1]
     assert oc.dbscan_labels(nb, 3).tolist() == [0, 0, 0, 0, -1]      # 0 and 3 are border points of cores 1 and 2
     assert oc.groups_from_labels([1, -1, 1, 0]) == [[0, 2], [1], [3]]
+
+
+def test_similarity_relationships_oracle_matches_reference(relationships_golden):
+    """core.py:3493-3531 -- the oracle reproduces the reference's graph exactly (same sklearn-order cosines,
+    same argsort tie behaviour)."""
+    rg = relationships_golden
+    all_feat = {}
+    for folder, x in rg["features"].items():
+        keep = [i for i in range(len(x)) if (i % 11) != 5]
+        all_feat[folder] = ([f"{folder}_{i:04d}" for i in keep], x[keep])
+    graph, _ = flat_ip.similarity_relationships(all_feat)
+    assert graph == rg["graph"]
