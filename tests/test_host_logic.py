@@ -172,3 +172,30 @@ def test_select_representative_frame_matches_reference(research_golden):
             assert [ff.select_representative_frame(g, emb, None) for g in groups] == case["representatives"][span]
             n += sum(len(g) > 1 for g in groups)
     assert n >= 20
+
+
+def test_temporal_and_cluster_wrappers_validate_before_touching_the_device():
+    """Argument handling that needs no GPU: same messages / early returns as the reference (core.py:3663-3670;
+    filter_research_update.py:115-116)."""
+    from ivr_b200.temporal import TemporalAnalyzer
+
+    class _Log:
+        def __init__(self):
+            self.warnings = []
+
+        def warning(self, msg):
+            self.warnings.append(msg)
+
+    log = _Log()
+    ta = TemporalAnalyzer(logger=log, device=0)
+    x = np.zeros((20, 8), np.float32)
+    with pytest.raises(ValueError, match="Features must be numpy arrays"):
+        ta.find_similar_sequences(x.tolist(), x)
+    with pytest.raises(ValueError, match="Features must be 2D arrays"):
+        ta.find_similar_sequences(x[0], x)
+    assert ta.find_similar_sequences(x[:3], x, sequence_length=5) == []
+    assert log.warnings == ["Insufficient features for sequence comparison"]
+    with pytest.raises(ValueError, match="Features must be numpy array"):
+        ta.detect_scene_boundaries(x.tolist())
+    assert ff.cluster_similar_frames([]) == [] and ff.cluster_similar_frames([x[0]]) == [[0]]
+    assert ff.select_representative_frame([7], [None] * 8) == 7
