@@ -5,12 +5,22 @@ Metric (BASELINE.json): top-100 queries/sec over N x 512 embeddings at 1/2/4/8 B
 roofline fraction of the dominant kernel.  Workload: BASELINE config D -- 100 M x 512 synthetic
 CLIP-like embeddings (fp16 rows, 102.4 GB: fits ONE B200), a batch of 4096 queries, k = 100.
 Scaling is STRONG: the same 100 M rows are row-sharded over the N ranks (N=8 -> 12.5 M rows per
-GPU, exactly config D), local top-k per GPU, one NCCL all-gather, on-device k-way merge.
+GPU, exactly config D), local top-k per GPU, one NCCL all-gather of packed 64-bit keys, on-device
+k-way merge.
 
     python bench.py --gpus 1 --steps K --warmup W          # our arm
-    python bench.py --impl reference ...                   # CPU flat search (oracle port of the
-                                                           # FAISS contract; FAISS itself is absent)
+    python bench.py --impl reference ...                   # the reference's own CPU code path
+
 A "step" is one pass of the hot path over one query batch.  Prints ONE JSON line (rank 0).
+
+Reference arm: the reference's OWN batched entry point, ``core.FAISSRetriever.build_index`` + ``.search``
+(core.py:758-930), imported unmodified from ``oracle/_ref`` (tools/make_ref.py) and run on every host core of
+the box.  FAISS -- the un-vendored, absent library under it -- is replaced by the oracle's multi-threaded
+restatement of the IndexFlatIP contract (oracle/flat_ip_mt.py).  A step is a BOUNDED sample of the workload
+(``--cpu-sample-queries`` of the queries x ``--cpu-sample-rows`` of the rows); q/s for the full workload are
+obtained by scaling the flat-search part linearly in rows (flat search is linear in N) and keeping the
+reference's per-hit Python loop as measured (it does not depend on N).  Both the sample and the split are
+printed.
 """
 from __future__ import annotations
 
@@ -23,6 +33,17 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # The CPU arm uses every host core it may run on.  Launchers (torch.distributed.run) export OMP_NUM_THREADS=1,
+    # which the OpenMP / BLAS pools read once at import: fix the environment BEFORE numpy / torch are imported
+    # (oracle/flat_ip_mt.set_threads() then also sets the counts explicitly at run time).
+    try:
+        _cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        _cores = os.cpu_count() or 1
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(_cores)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -32,7 +53,8 @@ if ROOT not in sys.path:
 METRIC = "top-100 queries/sec over Nx512 embeddings"
 GEN_CHUNK = 500_000              # rows generated per step; shard boundaries are multiples of it
 N_CENTRES = 4096
-CHECK_QUERIES = 8                # queries verified against an exact fp32 scan of the whole DB
+CHECK_QUERIES = 256              # queries verified against an exact fp32 scan of the whole DB
+TOL = 1e-3                       # north_star: ids identical except ties within 1e-3 of the k-th score
 
 
 def parse_args():
@@ -47,12 +69,21 @@ def parse_args():
     p.add_argument("--k", type=int, default=100)
     p.add_argument("--path", type=int, default=int(os.environ.get("IVR_BENCH_PATH", 0)),
                    help="0 auto, 1 streaming (K3), 2 tcgen05 (K1+K2)")
-    p.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    p.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     p.add_argument("--cpu-sample-queries", type=int, default=256)
+    p.add_argument("--cpu-dedup-frames", type=int, default=10_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true",
-                   help="skip the informational legs for BASELINE configs B (dedup) and C (single query)")
+                   help="skip the informational legs (BASELINE configs A, B, C, the production-shaped cell)")
     return p.parse_args()
+
+
+def workload_config(args):
+    """The SAME dict in both arms (driver: same_config)."""
+    return {"workload": f"BASELINE config D: flat inner-product top-{args.k} over {args.rows}x{args.dim} embeddings, "
+                        f"batch {args.nq}",
+            "rows": args.rows, "dim": args.dim, "nq": args.nq, "k": args.k, "n_gpus": args.gpus,
+            "cache": "inputs larger than L2 (every DB shard >> 126 MB); no L2 flush needed"}
 
 
 # ---------------------------------------------------------------------------- synthetic data
@@ -78,6 +109,17 @@ def gen_queries(nq, dim, cen_cpu):
     z = torch.randint(0, N_CENTRES, (nq,), generator=g)
     q = cen_cpu[z] + (0.5 / dim ** 0.5) * torch.randn(nq, dim, generator=g, dtype=torch.float32)
     return torch.nn.functional.normalize(q, dim=1)
+
+
+def gen_dedup_frames(n, d, dev, seed=7):
+    """Scenes of geometric length (mean 20) around a per-scene base vector, un-normalised fp32."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lens = torch.distributions.Geometric(probs=torch.tensor(1.0 / 20)).sample((n // 10 + 16,)).to(torch.int64) + 1
+    sid = torch.repeat_interleave(torch.arange(lens.numel()), lens)[:n].to(dev)
+    base = torch.randn(int(sid.max().item()) + 1, d, generator=g, device=dev)
+    sig = 0.10 + 0.25 * torch.rand(n, 1, generator=g, device=dev)
+    return ((base[sid] + sig * torch.randn(n, d, generator=g, device=dev)) * 3.0).contiguous()
 
 
 # ---------------------------------------------------------------------------- clocks sampler
@@ -123,13 +165,30 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------- CPU arm
-def cpu_flat_search_qps(xb_sample, xq, k, n_total, steps=1, warmup=0):
-    """Times the oracle port of the reference's CPU flat search (IndexFlatIP contract: fp32 sgemm
-    blocks + exact top-k, all host threads) on a bounded row sample, and extrapolates linearly in
-    the row count (flat search is linear in N)."""
-    from oracle import flat_ip
-    idx = flat_ip.IndexFlatIP(xb_sample.shape[1])
-    idx.add(xb_sample)
+def cpu_arm(args, xb, xq, steps, warmup):
+    """The reference's CPU path on this box's host cores (see the module docstring).  ``xb`` / ``xq`` are the
+    bounded sample (float32 NumPy).  Returns the ``cpu_baseline`` object plus ms_per_step of the sample."""
+    from oracle import flat_ip_mt, ref_runner, ref_shims
+    cores = flat_ip_mt.set_threads()                     # explicit: launchers export OMP_NUM_THREADS=1
+    n_s, nq_s, n_total, k = len(xb), len(xq), args.rows, args.k
+    grow = n_total / n_s
+    if ref_shims.reference_available():
+        r = ref_runner.time_faiss_retriever(xb, xq, k, steps=steps, warmup=warmup)
+        loop_s = max(r["step_s"] - r["search_s"], 0.0)
+        per_query = r["search_s"] / nq_s * grow + loop_s / nq_s
+        raw_qps = nq_s / (r["search_s"] * grow)
+        out = {"value": 1.0 / per_query, "unit": "queries/s", "cores": cores, "kind": "reference",
+               "what": "the reference's own core.FAISSRetriever.search (core.py:848-930, unmodified, from oracle/_ref) "
+                       "over oracle/flat_ip_mt.IndexFlatIP (FAISS, an un-vendored dependency, is absent)",
+               "sample": f"{nq_s} of {args.nq} queries x {n_s} of {n_total} rows per step "
+                         f"({r['step_s']:.2f} s of CPU work: {r['search_s']:.2f} s flat search on {cores} threads + "
+                         f"{loop_s:.2f} s of the reference's per-hit Python loop); flat-search time scaled x{grow:g} "
+                         f"in rows, the loop kept as measured",
+               "raw_flat_search": {"value": raw_qps, "unit": "queries/s", "kind": "port", "cores": cores,
+                                   "what": "oracle/flat_ip_mt alone: fp32 sgemm blocks + per-query top-k, all threads"}}
+        return out, r["step_s"] * 1e3
+    idx = flat_ip_mt.IndexFlatIP(xb.shape[1])
+    idx.add(xb)
     for _ in range(warmup):
         idx.search(xq[:8], k)
     ts = []
@@ -138,70 +197,131 @@ def cpu_flat_search_qps(xb_sample, xq, k, n_total, steps=1, warmup=0):
         idx.search(xq, k)
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    qps_sample = len(xq) / t
-    return qps_sample * (len(xb_sample) / n_total), t
+    return ({"value": nq_s / (t * grow), "unit": "queries/s", "cores": cores, "kind": "port",
+             "what": "oracle/flat_ip_mt (oracle/_ref is missing: run tools/make_ref.py where /root/reference exists)",
+             "sample": f"{nq_s} of {args.nq} queries x {n_s} of {n_total} rows per step ({t:.2f} s), scaled x{grow:g} in rows"},
+            t * 1e3)
 
 
-def host_threads():
-    try:
-        import torch
-        return int(os.environ.get("OMP_NUM_THREADS", 0)) or torch.get_num_threads()
-    except Exception:
-        return os.cpu_count() or 1
+def cpu_sample(args, device="cpu"):
+    import torch
+    dim = args.dim
+    cen = centres(dim, device)
+    n_s = min(args.cpu_sample_rows, args.rows)
+    ch = min(GEN_CHUNK, n_s)
+    xb = torch.cat([gen_rows(i, min(ch, n_s - i * ch), dim, cen, device).cpu()
+                    for i in range((n_s + ch - 1) // ch)]).numpy()
+    xq = gen_queries(args.nq, dim, cen.cpu())[:args.cpu_sample_queries].numpy()
+    return xb, xq
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    import torch
-    dim, k = args.dim, args.k
-    cen = centres(dim, "cpu")
-    n_s = min(args.cpu_sample_rows, args.rows)
-    xb = torch.cat([gen_rows(i, min(GEN_CHUNK, n_s - i * GEN_CHUNK), dim, cen, "cpu")
-                    for i in range((n_s + GEN_CHUNK - 1) // GEN_CHUNK)]).numpy()
-    xq = gen_queries(args.nq, dim, cen)[:args.cpu_sample_queries].numpy()
-    qps, t = cpu_flat_search_qps(xb, xq, k, args.rows, steps=args.steps, warmup=min(args.warmup, 1))
-    sample = (f"{len(xq)} of {args.nq} queries x {n_s} of {args.rows} rows per step, "
-              f"q/s extrapolated linearly in rows (x{n_s / args.rows:.4g})")
-    out = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+    if int(os.environ.get("RANK", 0)) != 0:
+        return                                            # the CPU arm runs once, on rank 0
+    xb, xq = cpu_sample(args)
+    cpu, ms = cpu_arm(args, xb, xq, args.steps, min(args.warmup, 1))
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "queries/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"BASELINE config D: flat inner-product top-{k} over {args.rows}x{dim} "
-                                  f"(fp32 rows on the host), batch {args.nq}",
-                      "rows": args.rows, "dim": dim, "nq": args.nq, "k": k,
-                      "note": "reference CPU path = oracle port of the faiss.IndexFlatIP contract "
-                              "(FAISS is an un-vendored dependency of the reference and is not installed)"},
-           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": host_threads(), "kind": "port",
-                            "sample": sample},
-           "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "config": workload_config(args), "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
 def measured_traffic(kernel, rows, dim, nq, k):
     """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu --set full
-    capture of the same shape (profiles/r1_traffic.json), per launch; None when no capture matches."""
-    try:
-        table = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-    except Exception:
-        return None
-    for e in table:
-        if (e["kernel"], e["rows"], e["dim"], e["nq"], e["k"]) == (kernel, rows, dim, nq, k):
-            return e["dram_bytes"]
+    captures of the same shape (profiles/*_traffic.json), per launch; None when no capture matches."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            table = json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+        for e in table:
+            if (e["kernel"], e["rows"], e["dim"], e["nq"], e["k"]) == (kernel, rows, dim, nq, k):
+                return e["dram_bytes"]
     return None
 
 
+def hbm_roofline(gbs, peaks, bytes_per_launch, **extra):
+    pk = peaks.get("hbm_gbs") or 6650.0
+    r = {"bound": "hbm", "achieved": gbs, "peak": pk, "unit": "GB/s", "frac": gbs / pk,
+         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
+         "algorithmic_bytes_per_launch": bytes_per_launch}
+    r.update(extra)
+    return r
+
+
+# ---------------------------------------------------------------------------- parity gate
+def parity_report(Dn, In, Dr, Ir, k):
+    """Ours (Dn, In) against the exact fp32 top-k (Dr, Ir) of the same queries over the whole DB.
+    Raises SystemExit on a violation of the north-star rule; returns the evidence otherwise."""
+    n_chk = len(In)
+    worst, subs = 0.0, 0
+    for q in range(n_chk):
+        ref = dict(zip(Ir[q].tolist(), Dr[q].tolist()))
+        s_k = Dr[q, -1]
+        for i_, d_ in zip(In[q].tolist(), Dn[q].tolist()):
+            if i_ in ref:
+                err = abs(ref[i_] - d_)
+                worst = max(worst, err)
+                if err > TOL:
+                    raise SystemExit(f"parity gate FAILED: q{q} id {i_} score {d_} vs exact {ref[i_]}")
+            else:                                            # not in the exact list: must be a tie at the k-th score
+                subs += 1
+                if d_ < s_k - TOL or d_ > s_k + 2 * TOL:
+                    raise SystemExit(f"parity gate FAILED: q{q} id {i_} score {d_} outside the tie band of s_k={s_k}")
+        must = Ir[q][Dr[q] > s_k + TOL]
+        miss = np.setdiff1d(must, In[q])
+        if miss.size:
+            raise SystemExit(f"parity gate FAILED: q{q} misses {miss.size} ids above s_k + tol")
+        if np.any(np.diff(Dn[q]) > 0):
+            raise SystemExit(f"parity gate FAILED: q{q} scores not sorted")
+    from oracle import comparator
+    return {"checked_queries": n_chk, "status": "ok", "tol": TOL,
+            "max_abs_score_error_vs_exact_fp32": worst,
+            "tie_band_substitutions": subs, "of_hits": n_chk * k,
+            "recall_vs_exact_fp32": comparator.recall_at_k(In, Ir)}
+
 
 # ---------------------------------------------------------------------------- extras (N=1 only)
-def run_extras(dev, peaks):
-    """Informational legs (not the headline): BASELINE config C (10 M x 768, single query, the
-    streaming kernel vs the HBM roofline) and config B (dedup 1 M x 512, W=8, thr 0.95)."""
+def time_device_search(idx, qd, k, reps=10, warm=3):
+    """Median whole-search device time (CUDA events on torch's stream) + the handle's own stage timing."""
+    import torch
+    for _ in range(warm):
+        idx.search_tensor(qd, k)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx.search_tensor(qd, k)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    idx.set_timing(True)
+    idx.search_tensor(qd, k)
+    t = idx.last_timing()
+    idx.set_timing(False)
+    return statistics.median(ts), t
+
+
+def time_host(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def run_extras(args, dev, peaks):
+    """Informational legs (not the headline): BASELINE configs A / B / C and the reference's production-shaped cell."""
     import ctypes as C
     import torch
     import ivr_b200
     from ivr_b200 import _native as nat
     out = {}
-    hbm = peaks.get("hbm_gbs") or 6650.0
+    k = 100
     # ---- config C: single-query latency path ------------------------------------------
     n, d = 10_000_000, 768
     cen = centres(d, dev)
@@ -209,58 +329,98 @@ def run_extras(dev, peaks):
     idx.reserve(n)
     for c in range(n // GEN_CHUNK):
         idx.add(gen_rows(c, GEN_CHUNK, d, cen, dev, seed=79))
-    q = gen_queries(1, d, cen.cpu())
-    qd = q.to(dev)
-    idx.set_timing(True)
-    ks = []
-    for i in range(13):
-        idx.search_tensor(qd, 100)
-        t = idx.last_timing()
-        if i >= 3:
-            ks.append(t["score_ms"] + t["merge_ms"] + t["prep_ms"])
-            kern = t["score_ms"]
-    idx.set_timing(False)
-    qn = q.numpy()
-    for _ in range(3):
-        idx.search(qn, 100)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        idx.search(qn, 100)
-    lat = (time.perf_counter() - t0) / 20
-    gbs = n * d * 2 / (kern * 1e-3) / 1e9
+    q = gen_queries(16, d, cen.cpu())
+    ms, t = time_device_search(idx, q[:1].to(dev), k)
+    qn = q[:1].numpy()
+    lat = time_host(lambda: idx.search(qn, k))
+    gbs = n * d * 2 / (t["score_ms"] * 1e-3) / 1e9
     out["config_c_single_query_10Mx768"] = {
-        "kernel": "search_stream_kernel", "kernel_ms": kern, "device_ms_per_query": statistics.median(ks),
+        "kernel": t["kernel"], "kernel_ms": t["score_ms"], "device_ms_per_query": ms,
         "e2e_latency_ms_host_buffers": lat * 1e3, "queries_per_s_e2e": 1.0 / lat,
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                     "algorithmic_bytes_per_launch": n * d * 2}}
-    # config C "also 2..16 queries": the small-batch tcgen05 kernel streams the rows once for the whole batch
-    q16 = gen_queries(16, d, cen.cpu()).to(dev)
-    idx.set_timing(True)
-    ks = []
-    for i in range(13):
-        idx.search_tensor(q16, 100)
-        t = idx.last_timing()
-        if i >= 3:
-            ks.append(t["score_ms"])
-    idx.set_timing(False)
-    kern = statistics.median(ks)
-    gbs = n * d * 2 / (kern * 1e-3) / 1e9
+        "roofline": hbm_roofline(gbs, peaks, n * d * 2)}
+    ms, t = time_device_search(idx, q.to(dev), k)
+    gbs = n * d * 2 / (t["score_ms"] * 1e-3) / 1e9
     out["config_c_16_queries_10Mx768"] = {
-        "kernel": t["kernel"], "kernel_ms": kern, "queries_per_s_device": 16 / (kern * 1e-3),
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                     "algorithmic_bytes_per_launch": n * d * 2,
-                     "note": "kernel_ms brackets the 2-3 seeded launches and their inter-launch merges"}}
+        "kernel": t["kernel"], "kernel_ms": t["score_ms"], "device_ms": ms, "queries_per_s_device": 16 / (ms * 1e-3),
+        "roofline": hbm_roofline(gbs, peaks, n * d * 2,
+                                 note="kernel_ms brackets the 2-3 seeded launches and their inter-launch merges")}
+    # ---- the reference's production-shaped cell: ONE query over 851 284 x 768, k = 50 (logs/performance.log:8) ----
+    n_p, k_p = 851_284, 50
+    pidx = ivr_b200.IndexFlatIP(d, device=dev.index)
+    pidx.reserve(n_p)
+    done = 0
+    while done < n_p:
+        m = min(GEN_CHUNK, n_p - done)
+        pidx.add(gen_rows(1000 + done // GEN_CHUNK, m, d, cen, dev, seed=79))
+        done += m
+    ms, t = time_device_search(pidx, q[:1].to(dev), k_p, reps=30)
+    u = ivr_b200.UnifiedIndex(device=dev.index)
+    u.faiss_index, u.is_loaded = pidx, True
+    u.metadata_list = [{"frame_id": i} for i in range(n_p)]
+    u.memory_maps = {"thumbnails": {}, "temporal": {}}
+    lat = time_host(lambda: u.search_vectors(qn[0], k=k_p), reps=50)
+    gbs = n_p * d * 2 / (ms * 1e-3) / 1e9
+    out["production_cell_851284x768_1query_k50"] = {
+        "kernel": t["kernel"], "device_ms": ms, "score_ms": t["score_ms"], "merge_ms": t["merge_ms"],
+        "search_vectors_host_to_host_ms": lat * 1e3,
+        "reference_logged_s": 7.23, "reference_source": "logs/performance.log:8 (text -> CLIP -> flat IP, first query)",
+        "roofline": hbm_roofline(gbs, peaks, n_p * d * 2, note="whole search (prep + stream + merge) vs the HBM peak")}
+    u.faiss_index = None
+    pidx.close()
     idx.close()
-    del idx
+    del idx, pidx
+    torch.cuda.empty_cache()
+    # ---- config A: 100 k x 512, 1000 queries (the only config quoted as the reference's CPU path) ----------
+    n, d = 100_000, 512
+    cen = centres(d, dev)
+    xa = gen_rows(0, n, d, cen, dev, seed=81)
+    qa = gen_queries(1000, d, cen.cpu())
+    aidx = ivr_b200.IndexFlatIP(d, device=dev.index)
+    aidx.add(xa)
+    ms, t = time_device_search(aidx, qa.to(dev), k)
+    qan = qa.numpy()
+    lat = time_host(lambda: aidx.search(qan, k), reps=10)
+    fl = 2.0 * n * d * 1000
+    out["config_a_100kx512_1000q"] = {
+        "kernel": t["kernel"], "device_ms": ms, "queries_per_s_device": 1000 / (ms * 1e-3),
+        "e2e_ms_host_buffers": lat * 1e3, "queries_per_s_e2e": 1000 / lat,
+        "tflops": fl / (ms * 1e-3) / 1e12,
+        "note": "102 GFLOP / 102 MB of rows: launch- and merge-latency bound, far below either roofline"}
+    # the legacy retriever wrapper, host to host (the reference needed 0.467 s, 96 % in its Python loop)
+    n_w = 20_000
+    raw = xa[:n_w].cpu().numpy()
+    kms = [ivr_b200.KeyframeMetadata(folder_name=f"L{i // 1000:02d}_V001", image_name=f"{i % 1000:04d}", frame_id=i % 1000,
+                                     file_path=f"keyframes/L{i // 1000:02d}_V001/{i % 1000:04d}.jpg", clip_features=raw[i])
+           for i in range(n_w)]
+    fr = ivr_b200.FAISSRetriever(device=dev.index)
+    fr.build_index(raw, kms, validate_consistency=False)
+    lat = time_host(lambda: fr.search(qan[:64], k=100), reps=5, warm=1)
+    out["faiss_retriever_wrapper_20kx512_64q_k100"] = {"host_to_host_s": lat, "hits": 6400,
+                                                       "reference_same_shape_s": 0.467,
+                                                       "reference_source": "SURVEY.md section 3.2 (authoring container)"}
+    if not args.no_cpu_baseline:
+        try:                                                 # the reference's own wrappers on config A, host cores
+            from oracle import flat_ip_mt, ref_runner, ref_shims
+            if ref_shims.reference_available():
+                cores = flat_ip_mt.set_threads()
+                xan = xa.cpu().numpy()
+                r = ref_runner.time_faiss_retriever(xan, qan, k)
+                sv = ref_runner.time_search_vectors(xan, qan[:200], k)
+                out["config_a_100kx512_1000q"]["cpu_baseline"] = {
+                    "kind": "reference", "cores": cores, "unit": "queries/s",
+                    "faiss_retriever_search": {"value": 1000 / r["step_s"], "seconds": r["step_s"],
+                                               "of_which_flat_search_s": r["search_s"]},
+                    "search_vectors_one_query_per_call": {"value": 200 / sv["loop_s"], "sample": "200 of the 1000 queries"},
+                    "what": "unmodified core.FAISSRetriever.search / unified_index.UnifiedIndex.search_vectors from "
+                            "oracle/_ref over oracle/flat_ip_mt (FAISS absent)"}
+        except Exception as e:
+            out["config_a_100kx512_1000q"]["cpu_baseline"] = {"error": repr(e)[:300]}
+    aidx.close()
+    del aidx, xa
     torch.cuda.empty_cache()
     # ---- config B: near-duplicate pruning ----------------------------------------------
     n, d, w = 1_000_000, 512, 8
-    g = torch.Generator(device=dev).manual_seed(7)
-    lens = torch.distributions.Geometric(probs=torch.tensor(1.0 / 20)).sample((n // 10,)).to(torch.int64) + 1
-    sid = torch.repeat_interleave(torch.arange(lens.numel()), lens)[:n].to(dev)
-    base = torch.randn(int(sid.max().item()) + 1, d, generator=g, device=dev)
-    sig = 0.10 + 0.25 * torch.rand(n, 1, generator=g, device=dev)
-    x = ((base[sid] + sig * torch.randn(n, d, generator=g, device=dev)) * 3.0).contiguous()
+    x = gen_dedup_frames(n, d, dev)
     cos = torch.empty(n, dtype=torch.float32, device=dev)
     mask = torch.empty(n, dtype=torch.int32, device=dev)
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -273,45 +433,53 @@ def run_extras(dev, peaks):
     ok = (ends - starts + 1) >= 2
     a, b = starts[ok].contiguous(), ends[ok].contiguous()
     nat.check(nat.lib.ivr_dedup_set_timing(1))
-    ms = (C.c_float * 2)()
-    best = None
-    for _ in range(8):
+    ms2 = (C.c_float * 2)()
+    runs = []
+    for _ in range(12):
         nat.check(nat.lib.ivr_dedup_window_device(dev.index, x.data_ptr(), n, d, a.data_ptr(), b.data_ptr(),
                                                   a.numel(), w, C.c_float(0.95), keep.data_ptr(), cos.data_ptr(),
                                                   mask.data_ptr(), st))
         torch.cuda.synchronize()
-        nat.check(nat.lib.ivr_dedup_last_timing(ms))
-        if best is None or ms[0] + ms[1] < best[0] + best[1]:
-            best = (ms[0], ms[1])
+        nat.check(nat.lib.ivr_dedup_last_timing(ms2))
+        runs.append((ms2[0], ms2[1]))
     nat.check(nat.lib.ivr_dedup_set_timing(0))
-    gbs = n * d * 4 / (best[0] * 1e-3) / 1e9
-    out["config_b_dedup_1Mx512_w8"] = {
-        "kernel": "banded_cosine_rw_kernel", "kernel_ms": best[0], "resolve_ms": best[1],
-        "frames_per_s": n / ((best[0] + best[1]) * 1e-3), "kept": int(keep.sum().item()), "scenes": int(a.numel()),
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                     "algorithmic_bytes_per_launch": n * d * 4}}
-    # CPU path beside it: the line-by-line port of filter.py's scene split + windowed rule (one Python thread by
-    # construction, like the reference) on a bounded slice of the same frames; parity of the slice checked on the way
-    try:
-        from oracle import dedup as od
-        ns = 100_000                                          # a 100 k-frame slice of config B
-        xs = x[:ns].cpu().numpy()
-        cfg = {"enable_similarity_filtering": True, "similarity_threshold": 0.95, "similarity_window_size": w,
-               "use_advanced_similarity_filtering": True, "min_frame_distance": 1}
-        t0 = time.perf_counter()
-        sims = od.calculate_similarities(list(xs))
-        scenes = od.group_into_scenes(od.detect_scene_transitions(sims, 0.75), ns, 2)
-        kept_cpu = od.apply_similarity_filtering_to_scenes(list(xs), list(range(ns)), scenes, cfg)[1]
-        t_cpu = time.perf_counter() - t0
-        from ivr_b200 import frame_filter as ffm
-        kept_gpu = ffm.FrameFilter(window=w, threshold=0.95, transition_threshold=0.75, min_scene_length=2).apply_filters(xs)
-        out["config_b_dedup_1Mx512_w8"]["cpu_baseline"] = {
-            "value": ns / t_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"first {ns} of {n} frames ({t_cpu:.1f} s of CPU work)",
-            "slice_parity": "ok" if list(kept_gpu) == list(kept_cpu) else
-                            f"differs ({len(kept_gpu)} vs {len(kept_cpu)} kept; unguarded synthetic data may sit on a threshold)"}
-    except Exception as e:                                       # informational leg only
-        out["config_b_dedup_1Mx512_w8"]["cpu_baseline"] = {"error": str(e)[:200]}
+    k_ms = statistics.median(r[0] for r in runs[2:])
+    r_ms = statistics.median(r[1] for r in runs[2:])
+    gbs = n * d * 4 / (k_ms * 1e-3) / 1e9
+    leg = {"kernel": "banded_cosine_rw_kernel", "kernel_ms": k_ms, "resolve_ms": r_ms,
+           "frames_per_s": n / ((k_ms + r_ms) * 1e-3), "kept": int(keep.sum().item()), "scenes": int(a.numel()),
+           "roofline": hbm_roofline(gbs, peaks, n * d * 4)}
+    # e2e: FrameFilter.apply_filters on PINNED host frames (2 GB H2D per call) -> kept indices on the host
+    xh = torch.empty((n, d), dtype=torch.float32).pin_memory()
+    xh.copy_(x)
+    xnp = xh.numpy()
+    ffl = ivr_b200.FrameFilter(window=w, threshold=0.95, transition_threshold=0.75, min_scene_length=2, device=dev.index)
+    kept_e2e = ffl.apply_filters(xnp)
+    t_e2e = time_host(lambda: ffl.apply_filters(xnp), reps=3, warm=1)
+    leg["e2e"] = {"value": n / t_e2e, "unit": "frames/s", "seconds": t_e2e, "h2d_bytes_per_step": n * d * 4,
+                  "d2h_bytes_per_step": int(n), "kept": int(len(kept_e2e)),
+                  "h2d_gbs": n * d * 4 / t_e2e / 1e9,
+                  "what": "FrameFilter.apply_filters(numpy float32 [n,d] in pinned host memory) -> kept indices"}
+    if not args.no_cpu_baseline:
+        try:                                                 # the reference's own filter.py on a bounded slice
+            from oracle import ref_runner, ref_shims
+            ns = min(args.cpu_dedup_frames, n)
+            xs = xnp[:ns]
+            if ref_shims.reference_available():
+                r = ref_runner.time_filter_pipeline(xs, window=w, threshold=0.95, transition=0.75, min_scene=2)
+                kept_gpu = ivr_b200.FrameFilter(window=w, threshold=0.95, transition_threshold=0.75, min_scene_length=2,
+                                                device=dev.index).apply_filters(np.ascontiguousarray(xs))
+                same = list(kept_gpu) == list(r["kept"])
+                leg["cpu_baseline"] = {
+                    "value": ns / r["seconds"], "unit": "frames/s", "cores": 1, "kind": "reference",
+                    "what": "unmodified filter.py (142-315) from oracle/_ref: calculate_similarities -> scenes -> "
+                            "filter_similar_frames_advanced; one Python thread by construction",
+                    "sample": f"first {ns} of {n} frames ({r['seconds']:.1f} s of CPU work)",
+                    "slice_parity": "ok (identical kept indices)" if same else
+                                    f"differs ({len(kept_gpu)} vs {len(r['kept'])} kept; unguarded synthetic data may sit on a threshold)"}
+        except Exception as e:
+            leg["cpu_baseline"] = {"error": repr(e)[:300]}
+    out["config_b_dedup_1Mx512_w8"] = leg
     return out
 
 
@@ -321,7 +489,6 @@ def run_ours(args):
     import torch.distributed as dist
     import ivr_b200
     from ivr_b200.sharded import ShardedFlatIP, partition_rows
-    from oracle import comparator
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -353,6 +520,7 @@ def run_ours(args):
     local.search_path = args.path
     local.reserve(row1 - row0)
     # build the shard + an exact fp32 top-k of the check queries over the SAME rows (the checker)
+    torch.backends.cuda.matmul.allow_tf32 = False
     best_d = torch.full((n_chk, k), -float("inf"), device=dev)
     best_i = torch.full((n_chk, k), -1, dtype=torch.int64, device=dev)
     t_build = time.perf_counter()
@@ -389,29 +557,8 @@ def run_ours(args):
         cd, ci = torch.cat(gd, 1), torch.cat(gi, 1)
         o = torch.argsort(cd, dim=1, descending=True, stable=True)[:, :k]
         best_d, best_i = torch.gather(cd, 1, o), torch.gather(ci, 1, o)
-    Dn, In = D[:n_chk].cpu().numpy(), I[:n_chk].cpu().numpy()
-    Dr, Ir = best_d.cpu().numpy(), best_i.cpu().numpy()
-    # comparator needs exact scores of OUR ids: every id we returned that the exact list also holds is
-    # looked up there; ids outside the exact top-k get the exact k-th score minus a margin check below
-    parity = "ok"
-    ref_map = [dict(zip(Ir[q].tolist(), Dr[q].tolist())) for q in range(n_chk)]
-    for q in range(n_chk):
-        s_k = Dr[q, -1]
-        for j, (i_, d_) in enumerate(zip(In[q], Dn[q])):
-            if int(i_) in ref_map[q]:
-                if abs(ref_map[q][int(i_)] - d_) > 1e-3:
-                    parity = f"FAILED: q{q} id {i_} score {d_} vs exact {ref_map[q][int(i_)]}"
-            elif d_ < s_k - 1e-3 or d_ > s_k + 2e-3:               # not in the exact list: must be a near-k tie
-                parity = f"FAILED: q{q} id {i_} score {d_} outside the tie band of s_k={s_k}"
-        must = Ir[q][Dr[q] > s_k + 1e-3]
-        miss = np.setdiff1d(must, In[q])
-        if miss.size:
-            parity = f"FAILED: q{q} misses {miss.size} ids above s_k+tol"
-        if np.any(np.diff(Dn[q]) > 0):
-            parity = f"FAILED: q{q} scores not sorted"
-    if parity != "ok":
-        raise SystemExit(f"parity gate failed on rank {rank}: {parity}")
-    recall = comparator.recall_at_k(In, Ir)
+    parity = parity_report(D[:n_chk].cpu().numpy(), I[:n_chk].cpu().numpy(), best_d.cpu().numpy(), best_i.cpu().numpy(), k)
+    del best_d, best_i
 
     # ---- value: whole-job throughput, inputs resident in HBM ---------------------------
     for _ in range(args.warmup):
@@ -443,6 +590,12 @@ def run_ours(args):
         launches = t
     local.set_timing(False)
     k_ms = statistics.mean(ks)
+    k_ranks = [k_ms]
+    if world > 1:                                                # straggler spread: every rank's own scoring time
+        kt = torch.tensor([k_ms], device=dev)
+        kall = [torch.empty_like(kt) for _ in range(world)]
+        dist.all_gather(kall, kt)
+        k_ranks = [float(v.item()) for v in kall]
     n_local = row1 - row0
     path = launches["path"]
     peaks = {}
@@ -452,66 +605,48 @@ def run_ours(args):
         pass
     if path == "mma" and launches["kernel"] == "search_mma_small_kernel":
         # small batches: the tcgen05 kernel streams every row once for the whole batch -> HBM-bound
-        pk = peaks.get("hbm_gbs") or 6650.0
         ach = (float(n_local) * dim * 2) / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk,
-                    "traffic": measured_traffic(launches["kernel"], n_local, dim, nq, k),
-                    "kernel": launches["kernel"], "kernel_ms": k_ms,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
-                    "algorithmic_bytes_per_launch": float(n_local) * dim * 2,
-                    "note": "kernel_ms brackets the 2-3 seeded launches of one search and their merges"}
+        roofline = hbm_roofline(ach, peaks, float(n_local) * dim * 2,
+                                traffic=measured_traffic(launches["kernel"], n_local, dim, nq, k),
+                                kernel=launches["kernel"], kernel_ms=k_ms,
+                                note="kernel_ms brackets the 2-3 seeded launches of one search and their merges")
     elif path == "mma":
         flops = 2.0 * n_local * dim * nq
-        sustained = k_ms >= 100.0
-        pk = peaks.get("bf16_tflops_sustained" if sustained else "bf16_tflops")
-        src = ("MEASURED_PEAKS.json " + ("bf16_tflops_sustained" if sustained else "bf16_tflops")) if pk else "fallback 1590 TFLOP/s"
-        pk = pk or 1590.0
+        burst, sust = peaks.get("bf16_tflops") or 1590.0, peaks.get("bf16_tflops_sustained") or 1400.0
         ach = flops / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+        # the scoring stage runs back to back inside a seconds-long loop under the 1 kW cap: the sustained cuBLAS
+        # figure is the comparable denominator; the burst fraction is printed beside it on every line
+        roofline = {"bound": "tensor", "achieved": ach, "peak": sust, "unit": "TFLOP/s", "frac": ach / sust,
+                    "frac_sustained": ach / sust, "frac_burst": ach / burst, "peak_burst": burst, "peak_sustained": sust,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / bf16_tflops" if peaks.get("bf16_tflops")
+                                   else "fallback 1400 / 1590 TFLOP/s",
                     "traffic": measured_traffic(launches["kernel"], n_local, dim, nq, k), "kernel": launches["kernel"],
-                    "kernel_ms": k_ms, "peak_source": src, "algorithmic_flops_per_launch": flops,
+                    "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                     "note": "kernel_ms brackets the whole scoring stage of one search: the short threshold-seeding "
-                            "launches (search_mma_kernel over 32k, 256k, 2M rows; ~3 %), their merges (<0.3 %) and "
-                            "the bulk launch"}
+                            "launches (~3 %), their merges (<0.3 %) and the bulk launch"}
     else:
         passes = (nq + 3) // 4
-        byts = float(n_local) * dim * 2 * passes                 # fp16 rows streamed once per 4-query pass
-        pk = peaks.get("hbm_gbs") or 6650.0
-        # events bracket only the first pass of a multi-pass search
-        ach = (float(n_local) * dim * 2) / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk,
-                    "traffic": measured_traffic("search_stream_kernel", n_local, dim, nq, k),
-                    "kernel": "search_stream_kernel", "kernel_ms": k_ms,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
-                    "algorithmic_bytes_per_launch": float(n_local) * dim * 2, "launches_per_step": passes,
-                    "bytes_per_step": byts}
+        ach = (float(n_local) * dim * 2) / (k_ms * 1e-3) / 1e9   # events bracket the first pass of a multi-pass search
+        roofline = hbm_roofline(ach, peaks, float(n_local) * dim * 2,
+                                traffic=measured_traffic("search_stream_kernel", n_local, dim, nq, k),
+                                kernel="search_stream_kernel", kernel_ms=k_ms, launches_per_step=passes)
+    roofline["kernel_ms_per_rank"] = {"min": min(k_ranks), "max": max(k_ranks), "all": k_ranks}
     per_step_launches = launches["score_launches"] + launches["merge_launches"] + launches["prep_launches"]
     if world > 1:
-        per_step_launches += 2                                   # pack + merge after the all-gather
+        per_step_launches += 1                                   # the key merge after the all-gather
 
     # ---- e2e: host buffers in, host results out, through the public API ----------------
     res_d = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     res_i = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     q_np = q_host.numpy()
 
-    debug = bool(os.environ.get("IVR_BENCH_DEBUG"))
-
     def e2e_step():
         if world == 1:
             return local.search(q_np, k)                         # C ABI with HOST pointers (H2D + D2H inside)
-        ta = time.perf_counter()
         qd = q_host.to(dev, non_blocking=True)
-        if debug:
-            torch.cuda.synchronize(); tb = time.perf_counter()
         D_, I_ = index.search(qd, k)
-        if debug:
-            torch.cuda.synchronize(); tc = time.perf_counter()
         res_d.copy_(D_, non_blocking=True); res_i.copy_(I_, non_blocking=True)
         torch.cuda.synchronize()
-        if debug and rank == 0:
-            td = time.perf_counter()
-            print(f"[e2e debug] h2d {1e3 * (tb - ta):.2f} ms, search {1e3 * (tc - tb):.2f} ms, d2h {1e3 * (td - tc):.2f} ms",
-                  file=sys.stderr, flush=True)
         return res_d, res_i
 
     for _ in range(args.warmup):
@@ -529,36 +664,31 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only, bounded sample) -------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = min(args.cpu_sample_rows, n_total)
-        xs = torch.cat([gen_rows(i, min(chunk_rows, n_s - i * chunk_rows), dim, cen, dev).cpu()
-                        for i in range((n_s + chunk_rows - 1) // chunk_rows)]).numpy()
-        xq = q_np[:args.cpu_sample_queries]
-        qps, t = cpu_flat_search_qps(xs, xq, k, n_total, steps=1, warmup=1)
-        cpu = {"value": qps, "unit": "queries/s", "cores": host_threads(), "kind": "port",
-               "sample": f"{len(xq)} queries x {n_s} of {n_total} rows ({t:.1f} s of CPU work), "
-                         f"q/s extrapolated linearly in rows"}
+        xb_s, xq_s = cpu_sample(args, dev)
+        cpu, _ = cpu_arm(args, xb_s, xq_s, steps=1, warmup=0)
+        del xb_s
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-               "config": {"workload": f"BASELINE config D: flat inner-product top-{k} over {n_total}x{dim} "
-                                      f"(fp16 rows, fp32 accumulate), batch {nq}, row-sharded over {world} GPU(s)",
-                          "rows": n_total, "rows_per_gpu": n_local, "dim": dim, "nq": nq, "k": k,
-                          "path": path, "parallelism": f"row-shard x{world} + all_gather + k-way merge",
-                          "cache": "inputs larger than L2 (DB shard >> 126 MB); no L2 flush needed",
-                          "build_s": round(t_build, 2)},
+               "config": workload_config(args),
+               "run": {"storage": "fp16 rows, fp32 accumulate", "rows_per_gpu": n_local, "path": path,
+                       "parallelism": f"row-shard x{world} + one all_gather of packed 64-bit keys + k-way merge",
+                       "build_s": round(t_build, 2)},
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                        "d2h_bytes_per_step": nq * k * 12},
                "gpu_launches": per_step_launches * args.steps,
                "roofline": roofline, "merge_ms": statistics.mean(merges),
-               "clocks": clocks, "parity": {"checked_queries": n_chk, "status": parity,
-                                            "recall_vs_exact_fp32": recall, "tol": 1e-3}}
+               "outside_scoring_ms": ms_step - max(k_ranks),
+               "clocks": clocks, "parity": parity}
         if cpu:
             out["cpu_baseline"] = cpu
         if world == 1 and not args.no_extras:
+            local.close()                                            # free the 102 GB shard before the side legs
+            torch.cuda.empty_cache()
             try:
-                out["extras"] = run_extras(dev, peaks)
+                out["extras"] = run_extras(args, dev, peaks)
             except Exception as e:                                   # informational legs never sink the headline
                 out["extras"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)

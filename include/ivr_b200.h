@@ -92,6 +92,14 @@ IVR_API int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t 
                             float* D_dev, int64_t* I_dev, int64_t id_offset, int path,
                             void* stream);
 
+/* Same search, result left as PACKED candidate keys for the cross-shard exchange (8 bytes per hit instead of
+ * 12): keys uint64 [nq, k] (device), key = order_preserving(float32 score) << 32 | ~(uint32)(row + id_offset),
+ * unsigned descending order = score descending then lower id, key 0 = padding (k > ntotal).  Global row ids
+ * must stay below 2^32 (id_offset + ntotal <= 2^32), else IVR_EUNSUPPORTED.  Merged by
+ * ivr_topk_merge_keys_device after one all-gather (semantic precedent: system.py:1721-1746). */
+IVR_API int ivr_index_search_keys_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
+                                 uint64_t* keys_dev, int64_t id_offset, int path, void* stream);
+
 /* Kernel timing of the LAST ivr_index_search_device call (CUDA events recorded on
  * the launching stream, only when enabled).  ms[0] = dominant scoring+select kernel,
  * ms[1] = top-k merge kernel(s), ms[2] = query preparation; launches[0..2] = launch
@@ -106,9 +114,14 @@ IVR_API const char* ivr_index_last_kernel(const ivr_index* idx);
 /* K5: merge per-shard top-k lists after the all-gather
  * (semantic precedent: system.py:1721-1746 concat + sort + truncate).
  *   D_parts float32 [n_parts, nq, k], I_parts int64 [n_parts, nq, k] (device),
- *   entries with id < 0 are padding.  Output descending, ties -> lower id. */
+ *   entries with id < 0 are padding; ids must be below 2^32 (the merge key holds a 32-bit id --
+ *   ShardedFlatIP refuses larger indexes).  Output descending, ties -> lower id. */
 IVR_API int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_parts, int n_parts,
                           int64_t nq, int k, float* D_out, int64_t* I_out, void* stream);
+/* The same merge on the packed keys of ivr_index_search_keys_device: keys_parts uint64 [n_parts, nq, k]
+ * (device; the all-gather output), n_parts <= 64.  No scratch, no allocation, one kernel launch. */
+IVR_API int ivr_topk_merge_keys_device(int device, const uint64_t* keys_parts, int n_parts, int64_t nq, int k,
+                               float* D_out, int64_t* I_out, void* stream);
 
 /* Replaces faiss.normalize_L2(x) (unified_index.py:1776): in-place row L2
  * normalisation, zero rows untouched. */

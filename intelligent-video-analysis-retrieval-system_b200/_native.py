@@ -44,12 +44,16 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_int]),
     "ivr_index_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "ivr_index_search_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                               C.c_int64, C.c_int, C.c_void_p]),
     "ivr_index_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ivr_index_last_timing": (C.c_int, [C.c_void_p, _c_f32p, _c_intp]),
     "ivr_index_last_path": (C.c_int, [C.c_void_p]),
     "ivr_index_last_kernel": (C.c_char_p, [C.c_void_p]),
     "ivr_topk_merge_device": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ivr_topk_merge_keys_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
     "ivr_normalize_l2": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "ivr_normalize_l2_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ivr_consecutive_cosine": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),

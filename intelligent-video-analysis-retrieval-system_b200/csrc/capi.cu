@@ -209,7 +209,7 @@ int ivr_index_add(ivr_index* idx, const float* x_host, int64_t n) {
     for (auto& ev : done) cudaEventDestroy(ev);
     if (rc == IVR_OK && e != cudaSuccess) { set_error("add: %s", cudaGetErrorString(e)); rc = IVR_ECUDA; }
     if (rc == IVR_ECUDA && g_err[0] == 0) set_error("add: CUDA failure");
-    if (rc == IVR_OK) idx->ntotal += n;
+    if (rc == IVR_OK) idx->ntotal += n;                          // the stream was drained above: rows are visible to every stream
     return rc;
 }
 
@@ -226,20 +226,40 @@ int ivr_index_device(const ivr_index* idx) { return idx ? idx->device : -1; }
 // --------------------------------------------------------------- search ----
 __global__ void fill_empty_kernel(float* D, int64_t* I, int64_t n) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (i < n) { D[i] = -3.402823466e+38f; I[i] = -1; }
+    if (i >= n) return;
+    if (D) { D[i] = -3.402823466e+38f; I[i] = -1; }
+    else I[i] = 0;                                   // packed-key output: key 0 = padding
 }
 
-int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
-                            int64_t* I_dev, int64_t id_offset, int path, void* stream) {
-    if (!idx || nq < 0 || (nq > 0 && (!q_dev || !D_dev || !I_dev))) {
-        set_error("search: bad argument");
-        return IVR_EINVAL;
+}  // extern "C"
+
+namespace ivr {
+
+// Which kernel family serves (nq, k) on this index.  IVR_PATH_AUTO: one query streams on the SIMT kernel; from two
+// queries up the tcgen05 kernels win (measured at 1 M .. 100 M rows, 512 / 768 dims) -- the small-batch kernel
+// wherever its resident query tile fits (any dimension), the batched kernels up to 1024 dims from three queries;
+// shapes neither tcgen05 kernel fits (e.g. dim > 1024 with a large batch) stream.
+static int choose_path(const ivr_index* idx, int64_t nq, int k, int path) {
+    const bool small_ok = mma_small_supported(idx, nq, k), big_ok = mma_supported(idx, nq, k);
+    if (path == IVR_PATH_AUTO)
+        return ((nq >= 2 && small_ok) || (nq > 2 && big_ok)) ? IVR_PATH_MMA : IVR_PATH_STREAM;
+    if (path == IVR_PATH_MMA && !small_ok && !big_ok) {
+        set_error("search: the tcgen05 path does not support dim=%d nq=%lld k=%d", idx->dim,
+                  static_cast<long long>(nq), k);
+        return IVR_EUNSUPPORTED;
     }
+    if (path != IVR_PATH_MMA && path != IVR_PATH_STREAM) { set_error("search: unknown path %d", path); return IVR_EINVAL; }
+    return path;
+}
+
+// D_dev == nullptr selects the packed-key output: I_dev then receives uint64 keys [nq, k]
+// (order_preserving(score) << 32 | ~(row + id_offset), 0 = padding) instead of int64 ids.
+static int search_device_impl(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                              int64_t* I_dev, int64_t id_offset, int path, cudaStream_t st) {
     if (k <= 0) { set_error("search: k must be positive (got %d)", k); return IVR_EINVAL; }
     if (k > IVR_MAX_K) { set_error("search: k=%d exceeds IVR_MAX_K=%d", k, IVR_MAX_K); return IVR_EUNSUPPORTED; }
     if (nq == 0) return IVR_OK;
     IVR_CUDA(cudaSetDevice(idx->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);       // NULL = the legacy default stream, as in CUDA
     if (idx->rows_ready_set) IVR_CUDA(cudaStreamWaitEvent(st, idx->rows_ready, 0));   // rows added on another stream
     idx->launches[0] = idx->launches[1] = idx->launches[2] = 0;
     idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = false;
@@ -250,24 +270,44 @@ int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int 
         idx->last_path = 0;
         return IVR_OK;
     }
-    int use = path;
-    // auto: one query streams on the SIMT kernel; from two queries up the tcgen05 kernels win (measured at
-    // 1 M .. 100 M rows, 512 / 768 dims) -- unless only the batched kernels fit the shape, which pay off from three
-    if (use == IVR_PATH_AUTO)
-        use = ((nq >= 2 && mma_small_supported(idx, nq, k)) || (nq > 2 && mma_supported(idx, nq, k))) ? IVR_PATH_MMA
-                                                                                                     : IVR_PATH_STREAM;
+    const int use = choose_path(idx, nq, k, path);
+    if (use < 0) return use;
     if (use == IVR_PATH_MMA) {
-        if (!mma_supported(idx, nq, k)) {
-            set_error("search: the tcgen05 path does not support dim=%d k=%d", idx->dim, k);
-            return IVR_EUNSUPPORTED;
-        }
         idx->last_path = IVR_PATH_MMA;
         return search_mma(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
     }
-    if (use != IVR_PATH_STREAM) { set_error("search: unknown path %d", path); return IVR_EINVAL; }
     idx->last_path = IVR_PATH_STREAM;
     idx->last_kernel = "search_stream_kernel";
     return search_stream(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
+}
+
+}  // namespace ivr
+
+extern "C" {
+
+int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
+                            int64_t* I_dev, int64_t id_offset, int path, void* stream) {
+    if (!idx || nq < 0 || (nq > 0 && (!q_dev || !D_dev || !I_dev))) {
+        set_error("search: bad argument");
+        return IVR_EINVAL;
+    }
+    // NULL = the legacy default stream, as in CUDA
+    return search_device_impl(idx, q_dev, nq, k, D_dev, I_dev, id_offset, path, static_cast<cudaStream_t>(stream));
+}
+
+int ivr_index_search_keys_device(ivr_index* idx, const float* q_dev, int64_t nq, int k, uint64_t* keys_dev,
+                                 int64_t id_offset, int path, void* stream) {
+    if (!idx || nq < 0 || (nq > 0 && (!q_dev || !keys_dev))) {
+        set_error("search_keys: bad argument");
+        return IVR_EINVAL;
+    }
+    if (id_offset < 0 || id_offset + idx->ntotal > 0x100000000ll) {
+        set_error("search_keys: global row ids must stay below 2^32 (offset %lld + %lld rows)",
+                  static_cast<long long>(id_offset), static_cast<long long>(idx->ntotal));
+        return IVR_EUNSUPPORTED;
+    }
+    return search_device_impl(idx, q_dev, nq, k, nullptr, reinterpret_cast<int64_t*>(keys_dev), id_offset, path,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k, float* D_host,
@@ -294,7 +334,7 @@ int ivr_index_search(ivr_index* idx, const float* q_host, int64_t nq, int k, flo
     int64_t* di = reinterpret_cast<int64_t*>(io + up(qb) + up(db));
     memcpy(pin, q_host, qb);
     IVR_CUDA(cudaMemcpyAsync(dq, pin, qb, cudaMemcpyHostToDevice, st));
-    IVR_TRY(ivr_index_search_device(idx, dq, nq, k, dd, di, 0, path, st));
+    IVR_TRY(search_device_impl(idx, dq, nq, k, dd, di, 0, path, st));
     IVR_CUDA(cudaMemcpyAsync(pin + up(qb), dd, db, cudaMemcpyDeviceToHost, st));
     IVR_CUDA(cudaMemcpyAsync(pin + up(qb) + up(db), di, ib, cudaMemcpyDeviceToHost, st));
     IVR_CUDA(cudaStreamSynchronize(st));
@@ -352,6 +392,28 @@ int ivr_topk_merge_device(int device, const float* D_parts, const int64_t* I_par
     }
     cudaFreeAsync(keys, st);
     return rc;
+}
+
+int ivr_topk_merge_keys_device(int device, const uint64_t* keys_parts, int n_parts, int64_t nq, int k,
+                               float* D_out, int64_t* I_out, void* stream) {
+    if (n_parts <= 0 || nq < 0 || k <= 0 || !keys_parts || !D_out || !I_out) {
+        set_error("topk_merge_keys: bad argument");
+        return IVR_EINVAL;
+    }
+    if (k > IVR_MAX_K) { set_error("topk_merge_keys: k=%d exceeds IVR_MAX_K", k); return IVR_EUNSUPPORTED; }
+    if (merge_tmp_entries(n_parts, nq, k) != 0) {     // one merge level needs no scratch: no allocation on this path
+        set_error("topk_merge_keys: at most 64 parts (got %d)", n_parts);
+        return IVR_EUNSUPPORTED;
+    }
+    if (nq == 0) return IVR_OK;
+    static thread_local int checked_device = -1;       // the capability probe is done once per thread and device
+    if (checked_device != device) { IVR_TRY(require_device(device)); checked_device = device; }
+    else IVR_CUDA(cudaSetDevice(device));
+    MergeIn in{};
+    in.entries = keys_parts; in.counts = nullptr;
+    in.list_stride = nq * k; in.q_stride = k;
+    in.n_lists = n_parts; in.fixed_count = k;
+    return merge_lists_final(in, nq, k, D_out, I_out, 0, nullptr, nullptr, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 // ------------------------------------------------------------ normalise ----

@@ -72,11 +72,14 @@ int ensure_capacity(ivr_index* idx, int64_t rows, cudaStream_t st, bool exact) {
         return IVR_ENOMEM;
     }
     if (idx->rows) {
+        // Earlier adds may have queued their fp32 -> fp16 conversion on OTHER streams (add_device runs on the
+        // caller's stream) and searches may still read the old block: drain the device before the copy, so the
+        // copy sees every row and nobody touches the block after it is freed.
+        IVR_CUDA(cudaDeviceSynchronize());
         if (idx->ntotal > 0)
             IVR_CUDA(cudaMemcpyAsync(nr, idx->rows, static_cast<size_t>(idx->ntotal) * row_bytes,
                                      cudaMemcpyDeviceToDevice, st));
         IVR_CUDA(cudaStreamSynchronize(st));
-        IVR_CUDA(cudaDeviceSynchronize());          // nobody may still read the old block
         IVR_CUDA(cudaFree(idx->rows));
     }
     idx->rows = nr;

@@ -35,6 +35,14 @@
 // Algorithmic work: 2 * ntotal * dpad * nq FLOP per search.
 #include "mma_common.cuh"
 
+// Pipeline probes (epilogue skipped / tcgen05.ld only) return garbage results: they exist only in builds made
+// with -DIVR_PROBES (tools/probe_epilogue.sh) and are compiled out of the shipped library.
+#ifdef IVR_PROBES
+#define IVR_SKIP_EPI(p) ((p).skip_epilogue)
+#else
+#define IVR_SKIP_EPI(p) 0
+#endif
+
 namespace ivr {
 
 
@@ -307,7 +315,7 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (q_ok && tau > tau_before) atomicMax(p.tau_g + q_global, f2ord(tau));   // share with the other CTAs
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
-            if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
+            if (IVR_SKIP_EPI(p) == 2) return;                        // perf probe: tcgen05.ld traffic only
             filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid);
         };
 
@@ -336,9 +344,9 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(set * kTileN);
                 uint32_t va[32], vb[32];
-                if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
+                if (IVR_SKIP_EPI(p) != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : kTileN / 32); c += 2) {
+                for (int c = 0; c < (IVR_SKIP_EPI(p) == 1 ? 0 : kTileN / 32); c += 2) {
                     make_room();
                     tmem_wait_ld(va);
                     tmem_ld_32x32(taddr + (c + 1) * 32, vb);
@@ -538,7 +546,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             if (q_ok && tau > tau_before) atomicMax(p.tau_g + q_global, f2ord(tau));
         };
         auto process_chunk = [&](uint32_t (&v)[32], int c, int64_t row0, int nvalid) {
-            if (p.skip_epilogue == 2) return;                        // perf probe: tcgen05.ld traffic only
+            if (IVR_SKIP_EPI(p) == 2) return;                        // perf probe: tcgen05.ld traffic only
             filter_chunk(v, tau, cnt, my_list, static_cast<uint32_t>(row0) + c * 32, c * 32, nvalid, TN);
         };
 
@@ -568,9 +576,9 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(set * TN);
             uint32_t va[32], vb[32];
-            if (p.skip_epilogue != 1) tmem_ld_32x32(taddr, va);
+            if (IVR_SKIP_EPI(p) != 1) tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < (p.skip_epilogue == 1 ? 0 : TN / 32); c += 2) {
+            for (int c = 0; c < (IVR_SKIP_EPI(p) == 1 ? 0 : TN / 32); c += 2) {
                 make_room();
                 tmem_wait_ld(va);
                 tmem_ld_32x32(taddr + (c + 1) * 32, vb);
@@ -692,7 +700,9 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
     p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
     if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;
     p.stagger = std::max(0, env_int("IVR_MMA_STAGGER", 1));
+#ifdef IVR_PROBES
     p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
+#endif
     {
         const int pol = env_int("IVR_MMA_ROW_POLICY", 0);          // 0 normal, 1 evict-first, 2 evict-last
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
@@ -743,7 +753,9 @@ static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int
     int grid = idx->sm_count / cg * cg;
     p.groups = grid / cg;
     if (p.nt < p.groups) { p.groups = static_cast<int>(std::max<int64_t>(p.nt, 1)); grid = p.groups * cg; }
+#ifdef IVR_PROBES
     p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
+#endif
     {
         const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
@@ -953,8 +965,13 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // measured (10 M rows): 512 dims -- 64 queries 2.0 ms small-batch vs 2.1 ms batched, 80: 2.5 vs 2.2, 128: 3.7 vs 2.3
     // (the resident queries squeeze the row ring); 768 dims -- 64..80 queries 2.4-2.6 ms vs 5.7-6.2 ms
     const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", idx->dpad <= kMaxKBlocks * kKBlock ? 64 : 128);
-    if (mode == 3 || (mode == 0 && nq <= small_max && mma_small_supported(idx, nq, k)))
+    // beyond 1024 dims only the small-batch kernel exists (its query tile loops over any number of k-blocks)
+    if (mode == 3 || ((mode == 0 || !mma_supported(idx, nq, k)) && nq <= small_max && mma_small_supported(idx, nq, k)))
         return search_mma_small(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
+    if (!mma_supported(idx, nq, k)) {
+        set_error("search_mma: dim=%d with %lld queries fits no tcgen05 kernel", idx->dim, static_cast<long long>(nq));
+        return IVR_EUNSUPPORTED;
+    }
     // measured (k=100, seeded launches): 4096 queries -- 3 M rows 11.6 ms query-tile-resident vs 11.5 ms
     // row-tile-resident, 10 M 38.7 vs 34.0, 100 M 405 vs 325; 1024 queries -- 10 M 8.4 vs 9.6.  The
     // row-tile-resident kernel moves 9x fewer bytes (the GPU is power-capped) but spreads a query over more
@@ -972,7 +989,7 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     }
     for (int64_t q0 = 0; q0 < nq; q0 += per_launch) {
         const int64_t b = std::min(per_launch, nq - q0);
-        IVR_TRY(search_mma_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev + q0 * k, I_dev + q0 * k, id_offset, st,
+        IVR_TRY(search_mma_batch(idx, q_dev + q0 * idx->dim, b, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset, st,
                                  cg, xres, q0 == 0));
     }
     return IVR_OK;

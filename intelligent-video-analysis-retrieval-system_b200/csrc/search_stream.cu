@@ -240,7 +240,7 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
         in.list_stride = static_cast<int64_t>(b) * C; in.q_stride = C;
         in.cnt_list_stride = b; in.cnt_q_stride = 1;
         in.n_lists = static_cast<int>(n_lists); in.fixed_count = 0;
-        IVR_TRY(merge_lists_final(in, b_real, k, D_dev + q0 * k, I_dev + q0 * k, id_offset, tmp,
+        IVR_TRY(merge_lists_final(in, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset, tmp,
                                   tmp_counts, st, &idx->launches[1]));
         if (idx->timing && q0 == 0) cudaEventRecord(idx->ev[3], st);
     }

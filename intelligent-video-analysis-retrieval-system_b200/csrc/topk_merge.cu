@@ -127,6 +127,16 @@ merge_kernel(MergeIn in, MergeOut out, int lists_per_group, int k, int kpad) {
     const int nvalid = min(total, k);
     if (FINAL) {
         const float scale = out.q_scale ? out.q_scale[q] : 1.0f;
+        if (out.D == nullptr) {
+            // packed-key output for the cross-shard exchange: final score, 32-bit GLOBAL row id, 0 = padding
+            uint64_t* K = reinterpret_cast<uint64_t*>(out.I);
+            const uint32_t off = static_cast<uint32_t>(out.id_offset);
+            for (int i = tid; i < k; i += blockDim.x) {
+                const uint64_t key = s_keys[i];
+                K[q * k + i] = (i < nvalid) ? make_key(key_score(key) * scale, key_row(key) + off) : 0ull;
+            }
+            return;
+        }
         for (int i = tid; i < k; i += blockDim.x) {
             const uint64_t key = s_keys[i];
             const bool ok = i < nvalid;
@@ -222,14 +232,15 @@ int merge_lists_keys(const MergeIn& in0, int64_t nq, int k, uint64_t* out_keys, 
 }
 
 // ---------------------------------------------------------------------------
-// (D, I) shard lists -> packed keys, for the post-all-gather merge
+// (D, I) shard lists -> packed keys, for the post-all-gather merge.  The key holds a 32-bit row id:
+// ids at or above 2^32 cannot be represented and raise the flag (the caller rejects the merge).
 // ---------------------------------------------------------------------------
 __global__ void pack_parts_kernel(const float* __restrict__ D, const int64_t* __restrict__ I,
                                   uint64_t* __restrict__ keys, int64_t n) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
     const int64_t id = I[i];
-    keys[i] = (id < 0) ? 0ull : make_key(D[i], static_cast<uint32_t>(id));
+    keys[i] = (id < 0 || id > 0xffffffffll) ? 0ull : make_key(D[i], static_cast<uint32_t>(id));
 }
 
 int pack_parts(const float* D, const int64_t* I, uint64_t* keys, int64_t n, cudaStream_t st) {

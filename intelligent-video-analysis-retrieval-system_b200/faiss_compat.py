@@ -136,6 +136,29 @@ class IndexFlatIP:
                 self.search_path if path is None else path, st))
         return D, I
 
+    def search_keys_tensor(self, q, k: int, id_offset: int = 0, out=None, path: int | None = None):
+        """Device-resident search that leaves the hits as packed 64-bit keys (int64 tensor [nq, k] holding
+        ``order_preserving(score) << 32 | ~(row + id_offset)``, 0 = padding): the 8-byte-per-hit payload of the
+        cross-shard exchange (``ShardedFlatIP``).  ``out`` may be a preallocated contiguous int64 [nq, k] tensor."""
+        import torch
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise ValueError(f"search(x): expected [nq,{self.d}], got {tuple(q.shape)}")
+        q = q.to(dtype=torch.float32).contiguous()
+        _check_device(q, self.device)
+        nq, k = q.shape[0], int(k)
+        if k <= 0:
+            raise ValueError("k must be positive")
+        if out is None:
+            out = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        elif out.shape != (nq, k) or out.dtype != torch.int64 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous int64 [nq, k] tensor")
+        if nq:
+            st = torch.cuda.current_stream(q.device).cuda_stream
+            nat.check(nat.lib.ivr_index_search_keys_device(
+                self._handle(), q.data_ptr(), nq, k, out.data_ptr(), int(id_offset),
+                self.search_path if path is None else path, st))
+        return out
+
     # -- instrumentation ---------------------------------------------------
     def set_timing(self, enable: bool = True):
         nat.check(nat.lib.ivr_index_set_timing(self._handle(), int(bool(enable))))

@@ -134,6 +134,8 @@ def filter_similar_frames_advanced(scene_embeddings, scene_indices, config):
     """filter.py:224-259: sliding-window rule against already-kept frames."""
     if not config["enable_similarity_filtering"] or len(scene_embeddings) <= 1:
         return scene_indices
+    if config["similarity_window_size"] <= 0:        # reference: range(i - 0, i) is empty -> nothing is ever compared
+        return scene_indices
     x, _ = _as_matrix(scene_embeddings)
     window = min(config["similarity_window_size"], len(x))
     keep, _ = _dedup_window(x, [(0, len(x) - 1)], min(window, len(x) - 1) or 1,
@@ -151,7 +153,9 @@ def apply_similarity_filtering_to_scenes(embeddings, valid_rows, scenes, config,
     kept_all: List[int] = []
     if scenes:
         x, _ = _as_matrix(embeddings)
-        if config.get("use_advanced_similarity_filtering", False):
+        if config.get("use_advanced_similarity_filtering", False) and config["similarity_window_size"] <= 0:
+            keep = np.ones(len(x), np.uint8)         # filter.py:233,242: an empty window keeps every frame
+        elif config.get("use_advanced_similarity_filtering", False):
             longest = max(e - s + 1 for s, e in scenes)
             window = max(1, min(config["similarity_window_size"], longest - 1 if longest > 1 else 1))
             keep, _ = _dedup_window(x, scenes, window, config["similarity_threshold"])
@@ -178,16 +182,19 @@ def extract_unique_frames_rule(embeddings, threshold: float = 0.98) -> List[int]
 
 
 def detect_scene_boundaries(features: np.ndarray, threshold: float = 0.3,
-                            min_scene_length: int = 5) -> List[Tuple[int, int]]:
-    """TemporalAnalyzer.detect_scene_boundaries (core.py:3584-3642)."""
-    if not isinstance(features, np.ndarray):
-        raise ValueError("Features must be numpy array")
-    if features.ndim != 2:
-        raise ValueError("Features must be 2D array")
+                            min_scene_length: int = 5, validate_inputs: bool = True) -> List[Tuple[int, int]]:
+    """TemporalAnalyzer.detect_scene_boundaries (core.py:3584-3642).  The type / shape checks AND the
+    "fewer than 2 * min_scene_length frames -> one scene" shortcut apply only with ``validate_inputs``
+    (core.py:3601-3608); without it a short clip gets real boundaries, as in the reference."""
+    if validate_inputs:
+        if not isinstance(features, np.ndarray):
+            raise ValueError("Features must be numpy array")
+        if features.ndim != 2:
+            raise ValueError("Features must be 2D array")
+        if len(features) < min_scene_length * 2:
+            return [(0, len(features) - 1)]
     n = len(features)
-    if n < min_scene_length * 2:
-        return [(0, n - 1)]
-    sims = calculate_similarities(features)
+    sims = calculate_similarities(features) if n > 1 else []
     bounds, start = [], 0
     for i, s in enumerate(sims):
         if s < threshold and i - start >= min_scene_length:
@@ -328,7 +335,12 @@ class FrameFilter:
             self.last_stats = {"original": 0, "filtered": 0, "removed": 0, "scenes": 0}
             return np.zeros(0, np.int64)
         longest = max(e - s + 1 for s, e in scenes)
-        keep, _ = _dedup_window(x, scenes, max(1, min(window, max(longest - 1, 1))), threshold, self.device)
+        if window <= 0:                              # filter.py:233,242: an empty window keeps every frame of every scene
+            keep = np.zeros(n, np.uint8)
+            for s, e in scenes:
+                keep[s:e + 1] = 1
+        else:
+            keep, _ = _dedup_window(x, scenes, max(1, min(window, max(longest - 1, 1))), threshold, self.device)
         kept = np.nonzero(keep)[0].astype(np.int64)
         orig = int(sum(e - s + 1 for s, e in scenes))
         self.last_stats = {"original": orig, "filtered": int(kept.size), "removed": orig - int(kept.size),

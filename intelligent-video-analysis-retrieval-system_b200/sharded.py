@@ -4,10 +4,14 @@ One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  The
 embedding matrix is partitioned into contiguous row blocks at ``add`` time:
 rank r owns global ids ``[offsets[r], offsets[r+1])``.  A search replicates the
 queries, runs the local exact top-k on every GPU with GLOBAL ids
-(``id_offset``), exchanges the ``[nq, k]`` (score, id) lists with ONE
-``all_gather`` and folds them with the on-device k-way merge kernel
-(``ivr_topk_merge_device``).  Exactness: the global top-k is a subset of the
-union of the local top-k lists.
+(``id_offset``) and leaves the hits as PACKED 64-bit keys (score and id in one
+word, 8 bytes per hit -- the form the local search already holds before its
+final unpack), exchanges the ``[nq, k]`` key lists with ONE
+``all_gather_into_tensor`` into a buffer the index owns, and folds them with the
+on-device k-way merge kernel (``ivr_topk_merge_keys_device``: one launch, no
+scratch, no allocation).  Exactness: the global top-k is a subset of the union
+of the local top-k lists.  The key holds a 32-bit id, so a sharded index is
+limited to 2^32 - 1 rows in total (checked at ``add``).
 
 Reference precedent for the semantics: ``_search_with_remote_index``
 concatenates the per-shard hit lists, sorts and truncates (system.py:1721-1746;
@@ -27,17 +31,20 @@ def partition_rows(n_total: int, world_size: int) -> np.ndarray:
     return np.array([(r * n_total) // world_size for r in range(world_size + 1)], dtype=np.int64)
 
 
+MAX_SHARDED_ROWS = (1 << 32) - 1          # the exchange key holds a 32-bit global row id
+
+
 def _cuda_merge(device: int):
     from . import _native as nat
 
-    def merge(D_parts, I_parts, k):
+    def merge(keys_parts, k):
         import torch
-        n_parts, nq, kk = D_parts.shape
-        D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
-        st = torch.cuda.current_stream(D_parts.device).cuda_stream
-        nat.check(nat.lib.ivr_topk_merge_device(device, D_parts.data_ptr(), I_parts.data_ptr(),
-                                                n_parts, nq, k, D.data_ptr(), I.data_ptr(), st))
+        n_parts, nq, kk = keys_parts.shape
+        D = torch.empty((nq, k), dtype=torch.float32, device=keys_parts.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=keys_parts.device)
+        st = torch.cuda.current_stream(keys_parts.device).cuda_stream
+        nat.check(nat.lib.ivr_topk_merge_keys_device(device, keys_parts.data_ptr(), n_parts, nq, k,
+                                                     D.data_ptr(), I.data_ptr(), st))
         return D, I
     return merge
 
@@ -46,8 +53,9 @@ class ShardedFlatIP:
     """Exact inner-product index row-sharded over the ranks of a process group.
 
     ``local_index`` / ``merge`` can be injected (the CPU ``gloo`` tests exercise the
-    partition / offset / gather logic with a stand-in backend); by default they are
-    the CUDA index and the CUDA merge kernel and fail loudly without a GPU.
+    partition / offset / gather logic with a stand-in backend that speaks the same packed-key
+    protocol: ``search_keys_tensor(q, k, id_offset, out)`` and ``merge(keys [world, nq, k], k)``);
+    by default they are the CUDA index and the CUDA merge kernel and fail loudly without a GPU.
     """
 
     def __init__(self, d: int, group=None, device: Optional[int] = None,
@@ -69,6 +77,8 @@ class ShardedFlatIP:
         self._merge = merge
         self.id_offset = 0
         self.ntotal_global = 0
+        self._keys = None          # [nq, k] local keys and [world, nq, k] gathered keys, reused across searches
+        self._gathered = None
 
     # ---- build ---------------------------------------------------------
     def add_global(self, x) -> None:
@@ -77,12 +87,16 @@ class ShardedFlatIP:
         off = partition_rows(n, self.world)
         if self.ntotal_global != 0:
             raise RuntimeError("add_global supports one contiguous build; use add_local to append")
+        if n > MAX_SHARDED_ROWS:
+            raise ValueError(f"a sharded index holds at most 2^32 - 1 rows in total (got {n})")
         self.id_offset = int(off[self.rank])
         self.local.add(x[off[self.rank]:off[self.rank + 1]])
         self.ntotal_global = n
 
     def add_local(self, x_local, id_offset: int, ntotal_global: int) -> None:
         """This rank's pre-partitioned block (e.g. generated on device), with its global offset."""
+        if int(ntotal_global) > MAX_SHARDED_ROWS:
+            raise ValueError(f"a sharded index holds at most 2^32 - 1 rows in total (got {ntotal_global})")
         if self.local.ntotal == 0:
             self.id_offset = int(id_offset)
         self.local.add(x_local)
@@ -98,15 +112,16 @@ class ShardedFlatIP:
         Returns (D [nq,k] float32 descending, I [nq,k] int64 global ids) on every rank."""
         import torch
         import torch.distributed as dist
-        D_loc, I_loc = self.local.search_tensor(q, k, id_offset=self.id_offset)
+        k = int(k)
         if self.world == 1:
-            return D_loc, I_loc
-        nq = D_loc.shape[0]
-        D_all = torch.empty((self.world * nq, k), dtype=D_loc.dtype, device=D_loc.device)
-        I_all = torch.empty((self.world * nq, k), dtype=I_loc.dtype, device=I_loc.device)
-        dist.all_gather_into_tensor(D_all, D_loc.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(I_all, I_loc.contiguous(), group=self.group)
-        return self._merge(D_all.view(self.world, nq, k), I_all.view(self.world, nq, k), int(k))
+            return self.local.search_tensor(q, k, id_offset=self.id_offset)
+        nq = q.shape[0]
+        if self._keys is None or self._keys.shape != (nq, k) or self._keys.device != q.device:
+            self._keys = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            self._gathered = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
+        self.local.search_keys_tensor(q, k, id_offset=self.id_offset, out=self._keys)
+        dist.all_gather_into_tensor(self._gathered.view(self.world * nq, k), self._keys, group=self.group)
+        return self._merge(self._gathered, k)
 
 
 # ---------------------------------------------------------------------------

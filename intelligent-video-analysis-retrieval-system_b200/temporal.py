@@ -30,12 +30,8 @@ class TemporalAnalyzer:
 
     def detect_scene_boundaries(self, features: np.ndarray, threshold: float = 0.3, min_scene_length: int = 5,
                                 validate_inputs: bool = True) -> List[Tuple[int, int]]:
-        if validate_inputs:
-            if not isinstance(features, np.ndarray):
-                raise ValueError("Features must be numpy array")
-            if features.ndim != 2:
-                raise ValueError("Features must be 2D array")
-        return ff.detect_scene_boundaries(features, threshold=threshold, min_scene_length=min_scene_length)
+        return ff.detect_scene_boundaries(features, threshold=threshold, min_scene_length=min_scene_length,
+                                          validate_inputs=validate_inputs)
 
     def find_similar_sequences(self, target_features: np.ndarray, database_features: np.ndarray,
                                sequence_length: int = 5, similarity_threshold: float = 0.8,

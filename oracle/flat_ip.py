@@ -179,6 +179,28 @@ def merge_shard_results(Ds, Is, k: int):
     return np.take_along_axis(cd, order, axis=1), np.take_along_axis(ci, order, axis=1)
 
 
+def pack_keys(D, I):
+    """CPU restatement of the 64-bit candidate key of csrc/common.cuh (``make_key``):
+    ``order_preserving(float32 score) << 32 | ~uint32(id)``; entries with id < 0 become key 0 (padding).
+    Unsigned descending key order == score descending, then lower id."""
+    u = np.ascontiguousarray(D, np.float32).view(np.uint32).astype(np.uint64)
+    o = np.where(u & np.uint64(0x80000000), ~u & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+    ids = np.asarray(I, np.int64)
+    low = (~ids.astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+    return np.where(ids < 0, np.uint64(0), (o << np.uint64(32)) | low)
+
+
+def unpack_keys(keys):
+    """Inverse of ``pack_keys``: (D float32, I int64); key 0 -> (-FLT_MAX, -1)."""
+    keys = np.asarray(keys, np.uint64)
+    o = (keys >> np.uint64(32)).astype(np.uint32)
+    u = np.where(o & np.uint32(0x80000000), o & np.uint32(0x7FFFFFFF), ~o)
+    D = u.astype(np.uint32).view(np.float32)
+    I = ((~keys) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    pad = keys == 0
+    return np.where(pad, np.float32(-3.402823466e+38), D).astype(np.float32), np.where(pad, -1, I)
+
+
 def similarity_relationships(all_features, top: int = 10, threshold: float = 0.7):
     """Restates MetadataManager._build_similarity_relationships (core.py:3493-3531) on
     {folder: (keys, float32 [n, d])}: sklearn-style cosine matrix per folder, for each frame the

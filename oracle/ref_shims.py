@@ -1,9 +1,11 @@
 """Import shims that run the REFERENCE'S OWN files in the authoring container.
 
-TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (and optional
-local cross-checks) to produce golden vectors from the unmodified reference at
-/root/reference.  Nothing here is read at run time on the GPU box, where
-/root/reference does not exist; no reference source is copied into the repo.
+TEST / BENCH INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden*.py to produce golden
+vectors from the unmodified reference at /root/reference, and -- through the byte-for-byte,
+git-ignored copy ``oracle/_ref`` that tools/make_ref.py makes at build time and that travels
+to the GPU box with the snapshot -- by ``bench.py``'s CPU arm (the reference's own wrappers
+and filter.py timed on the host cores) and by tests/test_dropin_gpu.py (the reference's own
+classes running on top of ``faiss_compat``).  No reference source enters the git history.
 
 What is shimmed and why:
   * ``transformers``  -- filter.py:46-48 calls ``from_pretrained`` at import
@@ -29,7 +31,19 @@ import sys
 import tempfile
 import types
 
-REFERENCE_DIR = os.environ.get("IVR_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference() -> str:
+    """IVR_REFERENCE_DIR, else /root/reference (authoring container), else oracle/_ref -- the byte-for-byte copy
+    tools/make_ref.py makes at build time, which is what exists on the GPU box."""
+    for cand in (os.environ.get("IVR_REFERENCE_DIR"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "filter.py")) and os.path.isfile(os.path.join(cand, "core.py")):
+            return cand
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def reference_available() -> bool:
@@ -80,11 +94,13 @@ def oracle_faiss_module():
 
 
 @contextlib.contextmanager
-def reference_modules(faiss_module=None, names=("filter",)):
+def reference_modules(faiss_module=None, names=("filter",), stub_transformers=False):
     """Yield a dict {name: module} of reference modules imported under shims.
 
     Modules are removed from ``sys.modules`` again on exit so the product's own
-    same-named modules are never shadowed.
+    same-named modules are never shadowed.  ``stub_transformers`` also stubs HuggingFace
+    for ``core`` (only its CLIP extractor uses it): saves ~20 s of import when just the
+    retriever classes are wanted.
     """
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_DIR}")
@@ -95,7 +111,7 @@ def reference_modules(faiss_module=None, names=("filter",)):
     old_cwd = os.getcwd()
     tmp = tempfile.mkdtemp(prefix="ivr_ref_")
     try:
-        if "filter" in names or "filter_research_update" in names:
+        if "filter" in names or "filter_research_update" in names or stub_transformers:
             sys.modules["transformers"] = _stub_transformers()
         if "filter_research_update" in names:       # filter_research_update.py:15,17 -- absent, presentation only
             sys.modules["imagehash"] = types.ModuleType("imagehash")

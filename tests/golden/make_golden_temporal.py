@@ -70,6 +70,18 @@ def main():
                                                 ta.detect_scene_boundaries(db, threshold=0.3, min_scene_length=5)]}
             print(name, "hits", len(hits), "best", sims[:3] if len(sims) else None,
                   "scenes", len(cases[name]["scene_boundaries"]))
+        # validate_inputs=False skips the "fewer than 2 * min_scene_length frames -> one scene" shortcut (core.py:3601-3608):
+        # every 9-frame slice of db "a" (min_scene_length 4 -> 9 >= 2 * 4 would not take the shortcut anyway; 5 does)
+        db = arrays["a_db"]
+        cases["short_clip"] = {"min_scene_length": 5, "threshold": 0.3, "length": 9, "slices": []}
+        for s0 in range(0, 120):
+            sl = db[s0:s0 + 9]
+            cases["short_clip"]["slices"].append({
+                "start": s0,
+                "validated": [[int(a), int(b)] for a, b in ta.detect_scene_boundaries(sl, 0.3, 5, validate_inputs=True)],
+                "unvalidated": [[int(a), int(b)] for a, b in ta.detect_scene_boundaries(sl, 0.3, 5, validate_inputs=False)]})
+        print("short_clip: slices whose unvalidated answer differs:",
+              sum(c["validated"] != c["unvalidated"] for c in cases["short_clip"]["slices"]))
         cases["short"] = {"hits": [[int(h[0]), float(h[1])] for h in
                                    ta.find_similar_sequences(arrays["a_target"][:3], arrays["a_db"], sequence_length=5)]}
         np.savez_compressed(os.path.join(HERE, "temporal.npz"), **arrays)

@@ -199,3 +199,44 @@ def test_temporal_and_cluster_wrappers_validate_before_touching_the_device():
         ta.detect_scene_boundaries(x.tolist())
     assert ff.cluster_similar_frames([]) == [] and ff.cluster_similar_frames([x[0]]) == [[0]]
     assert ff.select_representative_frame([7], [None] * 8) == 7
+
+
+def test_relationship_ranking_on_float32_cosines_reproduces_the_reference_graph(relationships_golden):
+    """relationships.rank_candidates (host stage of build_similarity_relationships): given the candidates an fp16-row
+    index would return (emulated here in NumPy), the float32 re-score + reference ordering reproduces the graph of
+    the unmodified MetadataManager._build_similarity_relationships (core.py:3493-3531) exactly."""
+    from ivr_b200.relationships import CANDIDATE_MARGIN, rank_candidates
+    rg = relationships_golden
+    n_keys = 0
+    for folder, x in rg["features"].items():
+        keep = [i for i in range(len(x)) if (i % 11) != 5]
+        if len(keep) < 2:
+            continue
+        keys = [f"{folder}_{i:04d}" for i in keep]
+        xk = x[keep].astype(np.float32)
+        nrm = np.sqrt(np.einsum("ij,ij->i", xk, xk, dtype=np.float32))
+        nrm[nrm == 0] = 1
+        xn = (xk / nrm[:, None]).astype(np.float32)
+        h = xn.astype(np.float16).astype(np.float32)                 # what the index stores
+        cand = np.argsort(-(h @ h.T), axis=1, kind="stable")[:, :min(11 + CANDIDATE_MARGIN, len(keys))]
+        for key, row in zip(keys, rank_candidates(xn, cand, 10, 0.7)):
+            assert [keys[j] for j in row] == rg["graph"][key], key
+            n_keys += 1
+        # the frame itself may be missing from the candidates (an fp16 near-duplicate outranked it): same result
+        cand_noself = np.where(cand == np.arange(len(keys))[:, None], -1, cand)
+        assert rank_candidates(xn, cand_noself, 10, 0.7) == rank_candidates(xn, cand, 10, 0.7)
+    assert n_keys == len(rg["graph"])
+
+
+def test_window_size_zero_keeps_every_frame_like_the_reference():
+    """filter.py:233,242: window_size = min(0, len) = 0 -> range(i, i) is empty -> nothing is compared, all frames kept.
+    Needs no device (nothing is computed)."""
+    from oracle import dedup as od
+    x = [np.full(8, 1.0, np.float32)] * 12                     # identical frames: any real window would drop 11 of them
+    for w in (0, -3):
+        cfg = ff.create_config(use_advanced_similarity_filtering=True, similarity_window_size=w)
+        assert ff.filter_similar_frames_advanced(x, list(range(100, 112)), cfg) == list(range(100, 112))
+        assert od.filter_similar_frames_advanced(x, list(range(100, 112)), cfg) == list(range(100, 112))
+        emb, rows, stats = ff.apply_similarity_filtering_to_scenes(x, list(range(12)), [(0, 4), (6, 11)], cfg)
+        want = od.apply_similarity_filtering_to_scenes(x, list(range(12)), [(0, 4), (6, 11)], cfg)
+        assert rows == want[1] == [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11] and stats == want[2]

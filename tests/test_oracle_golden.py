@@ -166,6 +166,21 @@ def test_sequence_oracle_matches_reference(temporal_golden, name):
     assert [list(b) for b in od.detect_scene_boundaries(db, 0.3, 5)] == case["scene_boundaries"]
 
 
+def test_scene_boundaries_short_clip_with_and_without_validation(temporal_golden):
+    """core.py:3601-3608: the 'too few features -> single scene' shortcut is part of validate_inputs.  120 nine-frame
+    slices run through the unmodified reference both ways (33 of them answer differently)."""
+    from oracle import dedup as od
+    sc, db = temporal_golden["cases"]["short_clip"], temporal_golden["arrays"]["a_db"]
+    differ = 0
+    for c in sc["slices"]:
+        sl = db[c["start"]:c["start"] + sc["length"]]
+        for flag, key in ((True, "validated"), (False, "unvalidated")):
+            got = od.detect_scene_boundaries(sl, sc["threshold"], sc["min_scene_length"], validate_inputs=flag)
+            assert [list(b) for b in got] == c[key], (c["start"], key)
+        differ += c["validated"] != c["unvalidated"]
+    assert differ >= 20
+
+
 def test_sequence_oracle_short_inputs_and_mean_order(temporal_golden):
     from oracle import temporal as ot
     tg = temporal_golden
@@ -223,3 +238,66 @@ def test_similarity_relationships_oracle_matches_reference(relationships_golden)
         all_feat[folder] = ([f"{folder}_{i:04d}" for i in keep], x[keep])
     graph, _ = flat_ip.similarity_relationships(all_feat)
     assert graph == rg["graph"]
+
+
+def test_multithreaded_cpu_baseline_matches_the_numpy_oracle():
+    """oracle/flat_ip_mt (the TIMED CPU baseline: torch sgemm + topk on every host thread) returns exactly what the
+    NumPy oracle returns -- ids, order (ties -> lower id), scores, -1 / -FLT_MAX padding."""
+    from oracle import flat_ip, flat_ip_mt, synth
+    for n, d, nq, k, blk in ((30_000, 64, 33, 100, 1 << 13), (5, 16, 3, 8, 4), (12_345, 128, 7, 50, 1 << 12)):
+        xb = synth.clip_like(n, d, seed=n, n_centres=32)
+        xq = synth.clip_like(nq, d, seed=n + 1, n_centres=32)
+        a = flat_ip.IndexFlatIP(d)
+        a.add(xb)
+        b = flat_ip_mt.IndexFlatIP(d, db_block=blk)
+        b.add(xb[:n // 2])
+        b.add(xb[n // 2:])
+        D, I = a.search(xq, k)
+        D2, I2 = b.search(xq, k)
+        assert np.array_equal(I, I2)
+        np.testing.assert_allclose(D2, D, rtol=0, atol=2e-6)
+    dup = np.tile(synth.gaussian_unit(10, 32, seed=5), (30, 1))      # exact ties across the k-th boundary: like FAISS,
+    a, b = flat_ip.IndexFlatIP(32), flat_ip_mt.IndexFlatIP(32, db_block=64)   # no promise WHICH tied row is returned
+    a.add(dup); b.add(dup)
+    (D, I), (D2, I2) = a.search(dup[:4], 40), b.search(dup[:4], 40)
+    np.testing.assert_allclose(D2, D, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(a.scores_of(dup[:4], I2), D2, rtol=0, atol=2e-6)
+    assert all(len(set(r.tolist())) == 40 for r in I2) and np.array_equal(I[:, :30], I2[:, :30])
+
+
+def test_key_packing_round_trip_and_order():
+    """oracle/flat_ip.pack_keys restates csrc/common.cuh make_key: unsigned descending key order == score descending,
+    then lower id; id < 0 -> key 0."""
+    from oracle import flat_ip
+    rng = np.random.default_rng(0)
+    D = rng.standard_normal((50, 40)).astype(np.float32)
+    D[0, :5] = [0.0, -0.0, 1e-38, -1e-38, np.float32(3.0)]
+    I = rng.integers(0, 2 ** 32 - 1, size=(50, 40), dtype=np.int64)
+    I[1, 3:9] = -1
+    keys = flat_ip.pack_keys(D, I)
+    D2, I2 = flat_ip.unpack_keys(keys)
+    ok = I >= 0
+    assert np.array_equal(I2[ok], I[ok]) and np.array_equal(D2[ok].view(np.uint32), D[ok].view(np.uint32))
+    assert (I2[~ok] == -1).all() and (keys[~ok] == 0).all()
+    for r in range(50):
+        order = np.argsort(keys[r])[::-1]
+        want = np.lexsort((np.where(I[r] < 0, 2 ** 40, I[r]), -D[r].astype(np.float64) + 0.0, I[r] < 0))
+        assert np.array_equal(D[r][order][ok[r][order]], D[r][want][ok[r][want]])
+
+
+def test_reference_copy_is_unmodified():
+    """oracle/_ref (git-ignored, made by tools/make_ref.py, shipped to the GPU box) is a byte-for-byte copy: its files
+    hash to the manifest written at copy time -- and, where the reference itself is present, to the originals."""
+    import hashlib
+    import json
+    import os
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)")
+    man = json.load(open(os.path.join(ref, "MANIFEST.json")))["sha256"]
+    assert {"core.py", "unified_index.py", "unified_builder.py", "filter.py", "utils.py"} <= set(man)
+    for name, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(ref, name), "rb").read()).hexdigest() == digest, name
+        orig = os.path.join("/root/reference", name)
+        if os.path.isfile(orig):
+            assert hashlib.sha256(open(orig, "rb").read()).hexdigest() == digest, name

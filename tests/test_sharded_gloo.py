@@ -28,9 +28,20 @@ class _OracleLocal:
         D, I = self.ix.search(q.numpy(), k)
         return torch.from_numpy(D), torch.from_numpy(np.where(I >= 0, I + id_offset, -1))
 
+    def search_keys_tensor(self, q, k, id_offset=0, out=None):
+        """The packed-key protocol of faiss_compat.IndexFlatIP.search_keys_tensor, restated on the CPU."""
+        D, I = self.ix.search(q.numpy(), k)
+        keys = torch.from_numpy(flat_ip.pack_keys(D, np.where(I >= 0, I + id_offset, -1)).view(np.int64))
+        if out is None:
+            return keys
+        out.copy_(keys)
+        return out
 
-def _merge(D_all, I_all, k):
-    D, I = flat_ip.merge_shard_results(list(D_all.numpy()), list(I_all.numpy()), k)
+
+def _merge(keys_parts, k):
+    parts = keys_parts.numpy().view(np.uint64)
+    D_all, I_all = zip(*(flat_ip.unpack_keys(p) for p in parts))
+    D, I = flat_ip.merge_shard_results(list(D_all), list(I_all), k)
     return torch.from_numpy(D), torch.from_numpy(I)
 
 

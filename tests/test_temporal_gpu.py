@@ -39,6 +39,20 @@ def test_find_similar_sequences_matches_reference_golden(temporal_golden, name):
     assert [list(b) for b in ta.detect_scene_boundaries(db, threshold=0.3, min_scene_length=5)] == case["scene_boundaries"]
 
 
+def test_scene_boundaries_short_clip_with_and_without_validation(temporal_golden):
+    """TemporalAnalyzer(validate_inputs=False) on a clip shorter than 2 * min_scene_length computes real boundaries,
+    like the reference (core.py:3601-3608) -- golden outputs of the unmodified reference, both ways."""
+    import ivr_b200
+    ta = ivr_b200.TemporalAnalyzer()
+    sc, db = temporal_golden["cases"]["short_clip"], temporal_golden["arrays"]["a_db"]
+    for c in sc["slices"]:
+        sl = np.ascontiguousarray(db[c["start"]:c["start"] + sc["length"]])
+        for flag, key in ((True, "validated"), (False, "unvalidated")):
+            got = ta.detect_scene_boundaries(sl, threshold=sc["threshold"], min_scene_length=sc["min_scene_length"],
+                                             validate_inputs=flag)
+            assert [list(b) for b in got] == c[key], (c["start"], key)
+
+
 @pytest.mark.parametrize("L,d,nt,nd", [(8, 128, 40, 20000), (1, 64, 5, 3000), (17, 100, 30, 5000), (128, 32, 130, 1500)])
 def test_find_similar_sequences_vs_oracle(L, d, nt, nd):
     import ivr_b200
