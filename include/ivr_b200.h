@@ -75,6 +75,10 @@ IVR_API int     ivr_index_destroy(ivr_index* idx);
 IVR_API int     ivr_index_reserve(ivr_index* idx, int64_t n_rows);           /* pre-size, avoids regrowth */
 IVR_API int     ivr_index_add(ivr_index* idx, const float* x_host, int64_t n);
 IVR_API int     ivr_index_add_device(ivr_index* idx, const float* x_dev, int64_t n, void* stream);
+/* Replaces index.reconstruct_n(first, n) -- what faiss.write_index / serialize_index store for a flat index
+ * (unified_index.py:1811; core.py:987): rows [first, first + n) as float32 [n, dim] (HOST pointer).  The values
+ * are the stored fp16 rows widened exactly, i.e. the added rows after one rounding to fp16. */
+IVR_API int     ivr_index_reconstruct(ivr_index* idx, int64_t first, int64_t n, float* x_host);
 IVR_API int     ivr_index_reset(ivr_index* idx);
 IVR_API int64_t ivr_index_ntotal(const ivr_index* idx);
 IVR_API int     ivr_index_dim(const ivr_index* idx);

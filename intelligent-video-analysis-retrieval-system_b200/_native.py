@@ -36,6 +36,7 @@ PROTOTYPES = {
     "ivr_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "ivr_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ivr_index_add_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ivr_index_reconstruct": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ivr_index_reset": (C.c_int, [C.c_void_p]),
     "ivr_index_ntotal": (C.c_int64, [C.c_void_p]),
     "ivr_index_dim": (C.c_int, [C.c_void_p]),

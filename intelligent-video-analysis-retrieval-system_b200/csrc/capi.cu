@@ -5,8 +5,29 @@
 #include <cstdarg>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 namespace ivr {
+
+// Pageable host memory <-> pinned staging.  One thread moves ~5-8 GB/s, a PCIe 5 x16 link ~50 GB/s: large blocks
+// are split over a few threads so that the staging copy does not throttle the H2D stream behind it.
+static void staged_memcpy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kMinPerThread = static_cast<size_t>(4) << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>({static_cast<size_t>(8), hw ? hw : 1, bytes / kMinPerThread});
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t o = t * per;
+        if (o >= bytes) break;
+        const size_t len = std::min(per, bytes - o);
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
 
 static thread_local char g_err[512] = "";
 
@@ -20,6 +41,7 @@ void set_error(const char* fmt, ...) {
 // other translation units
 int convert_rows(ivr_index* idx, const float* src_dev, int64_t n, int64_t dst_row, cudaStream_t st);
 int normalize_l2_device(float* x_dev, int64_t n, int d, cudaStream_t st);
+int reconstruct_rows(ivr_index* idx, int64_t first, int64_t n, float* dst_dev, cudaStream_t st);
 int pack_parts(const float* D, const int64_t* I, uint64_t* keys, int64_t n, cudaStream_t st);
 int dedup_set_timing(int enable);
 int dedup_last_timing(float ms[2]);
@@ -198,7 +220,7 @@ int ivr_index_add(ivr_index* idx, const float* x_host, int64_t n) {
         char* pin = static_cast<char*>(idx->pin) + b * chunk * row_bytes;
         float* dev = reinterpret_cast<float*>(static_cast<char*>(idx->ws) + b * chunk * row_bytes);
         if (it >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = IVR_ECUDA; break; }
-        memcpy(pin, x_host + off * idx->dim, m * row_bytes);
+        staged_memcpy(pin, x_host + off * idx->dim, m * row_bytes);
         if (cudaMemcpyAsync(dev, pin, m * row_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = IVR_ECUDA; break; }
         rc = convert_rows(idx, dev, m, idx->ntotal + off, st);
         if (rc != IVR_OK) break;
@@ -210,6 +232,60 @@ int ivr_index_add(ivr_index* idx, const float* x_host, int64_t n) {
     if (rc == IVR_OK && e != cudaSuccess) { set_error("add: %s", cudaGetErrorString(e)); rc = IVR_ECUDA; }
     if (rc == IVR_ECUDA && g_err[0] == 0) set_error("add: CUDA failure");
     if (rc == IVR_OK) idx->ntotal += n;                          // the stream was drained above: rows are visible to every stream
+    return rc;
+}
+
+int ivr_index_reconstruct(ivr_index* idx, int64_t first, int64_t n, float* x_host) {
+    if (!idx || first < 0 || n < 0 || (n > 0 && !x_host)) { set_error("reconstruct: bad argument"); return IVR_EINVAL; }
+    if (first + n > idx->ntotal) {
+        set_error("reconstruct: rows [%lld, %lld) outside the %lld stored", static_cast<long long>(first),
+                  static_cast<long long>(first + n), static_cast<long long>(idx->ntotal));
+        return IVR_EINVAL;
+    }
+    if (n == 0) return IVR_OK;
+    IVR_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    if (idx->rows_ready_set) IVR_CUDA(cudaStreamWaitEvent(st, idx->rows_ready, 0));
+    // fp16 -> fp32 on the device, then D2H through the two pinned half-buffers (the mirror image of ivr_index_add)
+    const size_t row_bytes = static_cast<size_t>(idx->dim) * sizeof(float);
+    int64_t chunk = std::max<int64_t>(1, (static_cast<int64_t>(32) << 20) / static_cast<int64_t>(row_bytes));
+    chunk = std::min(chunk, n);
+    IVR_TRY(ensure_pin(idx, 2 * chunk * row_bytes));
+    IVR_TRY(ensure_ws(idx, 2 * chunk * row_bytes));
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (auto& e : done)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            if (done[0]) cudaEventDestroy(done[0]);
+            set_error("reconstruct: cudaEventCreate failed");
+            return IVR_ECUDA;
+        }
+    int rc = IVR_OK;
+    int64_t off = 0, prev_off = 0, prev_m = 0;
+    for (int it = 0; ; ++it) {
+        const int b = it & 1;
+        int64_t m = 0;
+        if (off < n) {                                                 // queue chunk `it` ...
+            m = std::min(chunk, n - off);
+            char* pin = static_cast<char*>(idx->pin) + b * chunk * row_bytes;
+            float* dev = reinterpret_cast<float*>(static_cast<char*>(idx->ws) + b * chunk * row_bytes);
+            rc = reconstruct_rows(idx, first + off, m, dev, st);
+            if (rc != IVR_OK) break;
+            if (cudaMemcpyAsync(pin, dev, m * row_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = IVR_ECUDA; break; }
+            cudaEventRecord(done[b], st);
+        }
+        if (it > 0) {                                                  // ... while chunk `it - 1` is copied out
+            const int pb = (it - 1) & 1;
+            if (cudaEventSynchronize(done[pb]) != cudaSuccess) { rc = IVR_ECUDA; break; }
+            staged_memcpy(x_host + prev_off * idx->dim, static_cast<char*>(idx->pin) + pb * chunk * row_bytes, prev_m * row_bytes);
+        }
+        if (off >= n) break;
+        prev_off = off; prev_m = m;
+        off += m;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (auto& ev : done) cudaEventDestroy(ev);
+    if (rc == IVR_OK && e != cudaSuccess) { set_error("reconstruct: %s", cudaGetErrorString(e)); rc = IVR_ECUDA; }
+    if (rc == IVR_ECUDA && g_err[0] == 0) set_error("reconstruct: CUDA failure");
     return rc;
 }
 

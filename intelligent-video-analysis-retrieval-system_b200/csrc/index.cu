@@ -118,6 +118,28 @@ int convert_rows(ivr_index* idx, const float* src_dev, int64_t n, int64_t dst_ro
     return IVR_OK;
 }
 
+// fp16 [n, dpad] rows -> fp32 [n, dim] (exact widening; the padding columns are dropped)
+__global__ void rows_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t n, int dim, int dpad) {
+    const int64_t total = n * dim;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / dim;
+        const int c = static_cast<int>(i % dim);
+        dst[i] = __half2float(src[r * dpad + c]);
+    }
+}
+
+int reconstruct_rows(ivr_index* idx, int64_t first, int64_t n, float* dst_dev, cudaStream_t st) {
+    if (n <= 0) return IVR_OK;
+    const int64_t total = n * idx->dim;
+    const int threads = 256;
+    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, static_cast<int64_t>(idx->sm_count) * 16);
+    rows_to_f32_kernel<<<static_cast<unsigned>(blocks), threads, 0, st>>>(idx->rows + first * idx->dpad, dst_dev, n,
+                                                                          idx->dim, idx->dpad);
+    IVR_CUDA(cudaGetLastError());
+    return IVR_OK;
+}
+
 // In-place row L2 normalisation; one warp per row; zero rows untouched
 // (faiss.normalize_L2 / fvec_renorm_L2 semantics).
 __global__ void normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {

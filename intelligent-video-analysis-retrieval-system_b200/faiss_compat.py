@@ -100,6 +100,14 @@ class IndexFlatIP:
         st = torch.cuda.current_stream(x.device).cuda_stream
         nat.check(nat.lib.ivr_index_add_device(self._handle(), x.data_ptr(), x.shape[0], st))
 
+    def reconstruct_n(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """``faiss.Index.reconstruct_n``: rows [first, first + n) as float32 (the stored fp16 values, widened)."""
+        n = self.ntotal - first if n is None else int(n)
+        out = np.empty((n, self.d), np.float32)
+        if n:
+            nat.check(nat.lib.ivr_index_reconstruct(self._handle(), int(first), n, out.ctypes.data))
+        return out
+
     # -- search ----------------------------------------------------------
     def search(self, x, k: int):
         """D, I = index.search(x, k): float32 [nq,k] descending, int64 [nq,k], -1 padded."""
@@ -208,25 +216,114 @@ def index_gpu_to_cpu(index):
     return index
 
 
-# -- minimal persistence so reference save/load paths survive --------------
+# -- persistence in the FAISS on-disk layout -------------------------------------------------
+# The reference stores its index with ``faiss.write_index`` (unified_index.py:1811 -> the 'faiss_index' dataset of
+# a .rvdb; core.py:987 -> index.faiss) and restores it with ``faiss.deserialize_index`` / ``read_index``
+# (unified_index.py:1182-1188; core.py:1057, 4274-4278; system.py:2387).  For an ``IndexFlatIP`` the published
+# FAISS layout (faiss/impl/index_write.cpp: fourcc, write_index_header, WRITEXBVECTOR) is, little-endian:
+#
+#     offset  size  field
+#          0     4  fourcc "IxFI"  (inner product; "IxF2" = L2, "IxFl" = legacy flat)
+#          4     4  int32  d
+#          8     8  int64  ntotal
+#         16    16  int64  dummy, dummy   (FAISS writes 1 << 20 twice)
+#         32     1  bool   is_trained
+#         33     4  int32  metric_type    (0 = METRIC_INNER_PRODUCT, 1 = METRIC_L2)
+#         37     8  uint64 number of float32 values that follow (= ntotal * d)
+#         45   4*n  float32 rows, row-major
+#
+# FAISS itself is absent from this image, so the layout is pinned by a hand-built buffer in the tests, not by a
+# file FAISS wrote -- stated in DESIGN.md.
+_FLAT_HEADER = 45
+_FOURCC_IP, _FOURCC_L2, _FOURCC_LEGACY = b"IxFI", b"IxF2", b"IxFl"
+_IO_CHUNK_ROWS = 1 << 16
+
+
+def _flat_header(d: int, ntotal: int) -> bytes:
+    import struct
+    return (_FOURCC_IP + struct.pack("<iqqq?i", int(d), int(ntotal), 1 << 20, 1 << 20, True, METRIC_INNER_PRODUCT) +
+            struct.pack("<Q", int(ntotal) * int(d)))
+
+
+def _parse_flat_header(buf) -> tuple:
+    import struct
+    head = bytes(buf[:_FLAT_HEADER])
+    if len(head) < _FLAT_HEADER:
+        raise ValueError("not a FAISS index: shorter than a flat-index header")
+    fourcc = head[:4]
+    if fourcc == _FOURCC_L2:
+        raise NotImplementedError("the stored index is an IndexFlatL2; ivr_b200 implements inner product only")
+    if fourcc not in (_FOURCC_IP, _FOURCC_LEGACY):
+        raise NotImplementedError(f"unsupported FAISS index type {fourcc!r}: only IndexFlatIP ('IxFI') is read "
+                                  "(the reference forces every index type to FlatIP: core.py:1209-1219)")
+    d, ntotal, _d1, _d2, _trained, metric = struct.unpack("<iqqq?i", head[4:37])
+    (count,) = struct.unpack("<Q", head[37:45])
+    if metric != METRIC_INNER_PRODUCT:
+        raise NotImplementedError(f"metric_type {metric}: only METRIC_INNER_PRODUCT (0) is supported")
+    if d <= 0 or ntotal < 0 or count != ntotal * d:
+        raise ValueError(f"corrupt flat-index header: d={d} ntotal={ntotal} payload={count} floats")
+    return d, ntotal
+
+
+def _add_payload(index: "IndexFlatIP", payload: np.ndarray, ntotal: int, d: int) -> None:
+    rows = payload.reshape(ntotal, d)
+    index.reserve(ntotal)
+    for s in range(0, ntotal, 1 << 20):              # ivr_index_add streams each block through pinned double buffers
+        index.add(rows[s:s + (1 << 20)])
+
+
 def serialize_index(index: IndexFlatIP) -> np.ndarray:
-    """Not provided: index (de)serialisation is the .rvdb container I/O (unified_index.py:1182-1188), which is out of
-    scope; rebuild with ``IndexFlatIP.add`` from the stored embeddings instead."""
-    raise NotImplementedError(
-        "index (de)serialisation is .rvdb I/O, which is out of scope (SURVEY.md section 8f); "
-        "rebuild with IndexFlatIP.add from the stored embeddings instead")
+    """``faiss.serialize_index``: the index as a uint8 array in the FAISS IndexFlatIP layout (see above).  The
+    payload is what the index holds: the added rows after their one rounding to fp16."""
+    n, d = index.ntotal, index.d
+    out = np.empty(_FLAT_HEADER + 4 * n * d, np.uint8)
+    out[:_FLAT_HEADER] = np.frombuffer(_flat_header(d, n), np.uint8)
+    if n:
+        rows = out[_FLAT_HEADER:].view(np.float32).reshape(n, d)
+        nat.check(nat.lib.ivr_index_reconstruct(index._handle(), 0, n, rows.ctypes.data))
+    return out
 
 
-def deserialize_index(buf):
-    raise NotImplementedError(serialize_index.__doc__)
+def deserialize_index(buf, device: int | None = None) -> IndexFlatIP:
+    """``faiss.deserialize_index`` for the IndexFlatIP layout: uint8 array / bytes -> index on the GPU."""
+    a = np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else np.asarray(buf)
+    if a.dtype != np.uint8 or a.ndim != 1:
+        raise TypeError("deserialize_index expects a 1-D uint8 array (or bytes)")
+    d, ntotal = _parse_flat_header(a)
+    if a.size < _FLAT_HEADER + 4 * ntotal * d:
+        raise ValueError("truncated FAISS index: payload shorter than the header announces")
+    index = IndexFlatIP(d, device=device)
+    if ntotal:
+        payload = np.frombuffer(a, np.float32, count=ntotal * d, offset=_FLAT_HEADER) if a.flags.c_contiguous \
+            else np.ascontiguousarray(a[_FLAT_HEADER:_FLAT_HEADER + 4 * ntotal * d]).view(np.float32)
+        _add_payload(index, payload, ntotal, d)
+    return index
 
 
-def write_index(index, path):
-    raise NotImplementedError(serialize_index.__doc__)
+def write_index(index: IndexFlatIP, path) -> None:
+    """``faiss.write_index``: same bytes as ``serialize_index``, streamed to ``path`` in 64 k-row blocks."""
+    n, d = index.ntotal, index.d
+    with open(path, "wb") as f:
+        f.write(_flat_header(d, n))
+        blk = np.empty((min(_IO_CHUNK_ROWS, max(n, 1)), d), np.float32)
+        for s in range(0, n, _IO_CHUNK_ROWS):
+            m = min(_IO_CHUNK_ROWS, n - s)
+            nat.check(nat.lib.ivr_index_reconstruct(index._handle(), s, m, blk.ctypes.data))
+            f.write(memoryview(blk[:m]).cast("B"))
 
 
-def read_index(path, flags=0):
-    raise NotImplementedError(serialize_index.__doc__)
+def read_index(path, flags: int = 0, device: int | None = None) -> IndexFlatIP:
+    """``faiss.read_index`` for an IndexFlatIP file.  The float32 payload is memory-mapped (whatever ``flags`` says:
+    ``IO_FLAG_MMAP`` is how core.py:4274 asks for it) and streamed page cache -> pinned double buffer -> HBM by
+    ``ivr_index_add``, converted to fp16 rows on the device: no second host copy of the matrix is ever made."""
+    with open(path, "rb") as f:
+        d, ntotal = _parse_flat_header(f.read(_FLAT_HEADER))
+    index = IndexFlatIP(d, device=device)
+    if ntotal:
+        payload = np.memmap(path, dtype=np.float32, mode="r", offset=_FLAT_HEADER, shape=(ntotal * d,))
+        _add_payload(index, payload, ntotal, d)
+        del payload
+    return index
 
 
 def _is_cuda_tensor(x) -> bool:

@@ -240,3 +240,95 @@ def test_window_size_zero_keeps_every_frame_like_the_reference():
         emb, rows, stats = ff.apply_similarity_filtering_to_scenes(x, list(range(12)), [(0, 4), (6, 11)], cfg)
         want = od.apply_similarity_filtering_to_scenes(x, list(range(12)), [(0, 4), (6, 11)], cfg)
         assert rows == want[1] == [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11] and stats == want[2]
+
+
+def test_faiss_flat_index_header_layout():
+    """The 45-byte IndexFlatIP header faiss_compat writes and parses (faiss/impl/index_write.cpp: fourcc,
+    write_index_header, WRITEXBVECTOR), pinned field by field on a hand-built buffer.  No device needed."""
+    import struct
+    from ivr_b200 import faiss_compat as fc
+    h = fc._flat_header(768, 851_284)
+    assert len(h) == 45 and h[:4] == b"IxFI"
+    assert struct.unpack("<i", h[4:8]) == (768,) and struct.unpack("<q", h[8:16]) == (851_284,)
+    assert struct.unpack("<qq", h[16:32]) == (1 << 20, 1 << 20)
+    assert h[32:33] == b"\x01" and struct.unpack("<i", h[33:37]) == (0,)
+    assert struct.unpack("<Q", h[37:45]) == (851_284 * 768,)
+    assert fc._parse_flat_header(h) == (768, 851_284)
+    with pytest.raises(NotImplementedError, match="IndexFlatL2"):
+        fc._parse_flat_header(b"IxF2" + h[4:])
+    with pytest.raises(NotImplementedError, match="unsupported FAISS index type"):
+        fc._parse_flat_header(b"IwFl" + h[4:])
+    with pytest.raises(ValueError, match="corrupt"):
+        fc._parse_flat_header(h[:37] + struct.pack("<Q", 5))
+    with pytest.raises(ValueError, match="shorter"):
+        fc._parse_flat_header(h[:20])
+
+
+class _OracleBackedRetriever:
+    """ivr_b200.FAISSRetriever with the device index swapped for the NumPy oracle: exercises the HOST logic
+    (validation, id maps, batched re-score, rank / flattening) without a GPU."""
+
+    def __new__(cls):
+        import ivr_b200
+        from oracle import flat_ip
+
+        class R(ivr_b200.FAISSRetriever):
+            def _create_index(self, index_type, features):
+                return flat_ip.IndexFlatIP(features.shape[1])
+        return R()
+
+
+def test_retriever_host_logic_reproduces_the_reference_outputs(search_golden):
+    """The vectorised re-score (one gather + one batched dot for all nq * k hits) against the golden outputs of the
+    reference's per-hit loop (core.py:899-924): same hits, same order, same 1-based ranks, cosines within 1e-6."""
+    import ivr_b200
+    sg = search_golden
+    raw = (sg["xb"] * np.float32(2.5)).astype(np.float32)
+    kms = [ivr_b200.KeyframeMetadata(folder_name=m["folder_name"], image_name=m["image_name"], frame_id=m["frame_id"],
+                                     file_path=m["file_path"], clip_features=(raw[i] if i % 7 else None))
+           for i, m in enumerate(sg["meta"])]
+    fr = _OracleBackedRetriever()
+    fr.build_index(raw, kms, validate_consistency=False)
+    out = fr.search(sg["xq"][:3] * np.float32(1.7), k=12)
+    want = sg["results"]["faiss_retriever_search"]
+    assert [(r.metadata.folder_name, r.metadata.image_name, r.rank) for r in out] == [(w[0], w[1], w[3]) for w in want]
+    np.testing.assert_allclose([r.similarity_score for r in out], [w[2] for w in want], rtol=0, atol=1e-6)
+    assert all(r.query_relevance == r.similarity_score and r.temporal_context == [] for r in out)
+    assert any(r.similarity_score == 0.0 for r in out) or all(w[2] > 0 for w in want)      # frames without features score 0.0
+    one = fr.search(sg["xq"][4], k=5)                                                       # 1-D query
+    assert [(r.metadata.folder_name, r.metadata.image_name, r.rank) for r in one] == \
+        [(w[0], w[1], w[3]) for w in sg["results"]["faiss_retriever_search_1d"]]
+    by_id = sg["results"]["faiss_retriever_search_by_id"]
+    hits = fr.search_by_id(by_id["key"], k=7)
+    assert [(r.metadata.folder_name, r.metadata.image_name, r.rank) for r in hits] == [(h[0], h[1], h[3]) for h in by_id["hits"]]
+    np.testing.assert_allclose([r.similarity_score for r in hits], [h[2] for h in by_id["hits"]], rtol=0, atol=1e-6)
+    assert fr.search_by_id("no_such_key") == []
+    # validate_results: a frame whose metadata went bad after the build is skipped, the ranks of the others keep their gaps
+    victim = out[1].metadata
+    victim.file_path = ""
+    again = fr.search(sg["xq"][:1] * np.float32(1.7), k=12)
+    assert victim not in [r.metadata for r in again] and [r.rank for r in again] == [1] + list(range(3, 13))
+    assert len(fr.search(sg["xq"][:1] * np.float32(1.7), k=12, validate_results=False)) == 12
+    victim.file_path = "restored.jpg"
+    # argument errors carry the reference's messages
+    with pytest.raises(ValueError, match="Query dimension"):
+        fr.search(np.zeros((1, 3), np.float32) + 1, k=3)
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        fr.search(np.full((1, raw.shape[1]), np.nan, np.float32), k=3)
+    with pytest.raises(ValueError, match="1D or 2D"):
+        fr.search(np.zeros((1, 1, raw.shape[1]), np.float32), k=3)
+    with pytest.raises(RuntimeError, match="Index not trained"):
+        ivr_b200.FAISSRetriever().search(raw[:1], k=3)
+    with pytest.raises(ValueError, match="Features count"):
+        fr.build_index(raw[:5], kms[:4])
+    with pytest.raises(ValueError, match="Duplicate metadata key"):
+        fr.build_index(raw[:2], [kms[0], kms[0]])
+    for field, msg in (("folder_name", "folder_name must be a non-empty string"), ("frame_id", "frame_id must be an integer"),
+                       ("file_path", "file_path must be a non-empty string")):
+        kw = dict(folder_name="f", image_name="i", frame_id=1, file_path="p")
+        kw[field] = None
+        with pytest.raises(ValueError, match=msg):
+            ivr_b200.KeyframeMetadata(**kw)
+    assert ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], None) == 0.0
+    assert abs(ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], 3 * raw[1]) - 1.0) < 1e-6
+    assert ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], -raw[1]) == 0.0            # clamped

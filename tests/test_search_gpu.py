@@ -437,11 +437,13 @@ def test_dims_beyond_1024_pick_a_kernel_that_fits(d, nq):
     xq = synth.clip_like(nq, d, seed=94, n_centres=32)
     idx, ref = build(xb)
     check(idx, ref, xq, 20, path=0)
-    small_fits = 2 <= nq and ((nq + 15) // 16 * 16) * ((d + 63) // 64 * 64) * 2 <= 128 * 1024
+    tile_fits = ((nq + 15) // 16 * 16) * ((d + 63) // 64 * 64) * 2 <= 128 * 1024     # resident query tile <= 128 KB
+    small_fits = 2 <= nq and tile_fits                               # one query streams on the SIMT kernel
     t = idx.last_timing()
     assert t["kernel"] == ("search_mma_small_kernel" if small_fits else "search_stream_kernel"), t
-    if small_fits:
+    if tile_fits:
         check(idx, ref, xq, 20, path=2)                              # forcing the tcgen05 path works too
+        assert idx.last_timing()["kernel"] == "search_mma_small_kernel"
     else:
         idx.search_path = 2
         with pytest.raises(ivr_b200._native.NativeError):
@@ -691,3 +693,45 @@ def test_row_tile_resident_large_k_runs_in_several_query_batches(monkeypatch):
     idx, ref = build(xb)
     check(idx, ref, xq, 2048, path=2)
     assert idx.last_timing()["kernel"] == "search_mma_xres_kernel"
+
+
+def test_faiss_layout_serialisation_round_trip_through_the_device(tmp_path):
+    """faiss_compat.serialize_index / deserialize_index / write_index / read_index in the FAISS IndexFlatIP layout
+    ('IxFI' header + float32 payload): a hand-built buffer loads and searches like the rows it holds, and a round trip
+    through the device reproduces the fp16-rounded rows bit for bit."""
+    import struct
+    import ivr_b200
+    fc = ivr_b200.faiss_compat
+    n, d = 70_000, 96                                             # d not a multiple of 64: padded columns are dropped again
+    xb = synth.clip_like(n, d, seed=97, n_centres=64)
+    xq = synth.clip_like(5, d, seed=98, n_centres=64)
+    buf = (b"IxFI" + struct.pack("<iqqq?i", d, n, 1 << 20, 1 << 20, True, 0) + struct.pack("<Q", n * d) + xb.tobytes())
+    idx = fc.deserialize_index(np.frombuffer(buf, np.uint8))      # what unified_index.py:1182 passes
+    ref = flat_ip.IndexFlatIP(d)
+    ref.add(xb)
+    assert idx.ntotal == n and idx.d == d
+    check(idx, ref, xq, 50)
+    rows16 = xb.astype(np.float16).astype(np.float32)
+    assert np.array_equal(idx.reconstruct_n(0, n), rows16)
+    assert np.array_equal(idx.reconstruct_n(n - 7, 7), rows16[-7:])
+    out = fc.serialize_index(idx)
+    assert out.dtype == np.uint8 and bytes(out[:45]) == buf[:45]
+    assert np.array_equal(out[45:].view(np.float32).reshape(n, d), rows16)
+    again = fc.deserialize_index(out)
+    assert np.array_equal(fc.serialize_index(again), out)         # idempotent after the first rounding
+    path = tmp_path / "index.faiss"
+    fc.write_index(idx, str(path))
+    assert path.read_bytes() == out.tobytes()
+    back = fc.read_index(str(path), fc.IO_FLAG_MMAP)
+    assert back.ntotal == n
+    D1, I1 = idx.search(xq, 20)
+    D2, I2 = back.search(xq, 20)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+    empty = fc.deserialize_index(fc.serialize_index(fc.IndexFlatIP(d)))
+    assert empty.ntotal == 0 and empty.d == d
+    with pytest.raises(NotImplementedError):
+        fc.deserialize_index(np.frombuffer(b"IxF2" + buf[4:], np.uint8))
+    with pytest.raises(ValueError):
+        fc.deserialize_index(np.frombuffer(buf[:-8], np.uint8))
+    with pytest.raises(ivr_b200._native.NativeError):
+        idx.reconstruct_n(n - 1, 5)
