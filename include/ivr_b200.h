@@ -158,6 +158,22 @@ IVR_API int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, i
                             int64_t n_scenes, int window, float thr,
                             uint8_t* keep_dev, float* cos_prev_dev, uint32_t* mask_ws_dev,
                             void* stream);
+/* The whole similarity stage of filter.py in ONE call on host frames -- calculate_similarities ->
+ * detect_scene_transitions -> group_into_scenes -> apply_similarity_filtering_to_scenes with
+ * filter_similar_frames_advanced (filter.py:142-176, 224-315); what README's FrameFilter.apply_filters names:
+ *   e_host   float32 [n, d] raw (un-normalised) frame embeddings.  Page-locked memory is copied from directly;
+ *            pageable memory is staged through pinned double buffers by a few host threads.  Either way the
+ *            frames cross PCIe ONCE, in 64 MB chunks, each chunk's banded-cosine kernel queued behind its copy.
+ *   scenes   frame i starts a scene iff i == 0 or cos(e_i, e_{i-1}) < transition_thr (strict); scenes shorter
+ *            than min_scene_len are dropped (keep = 0), exactly like group_into_scenes.
+ *   rule     inside a scene keep the first frame; drop frame i iff an already KEPT j in [i - window, i) has
+ *            cos(e_i, e_j) >= thr; window <= 0 keeps every frame of every scene (filter.py:233, 242).
+ *   outputs  keep_host uint8 [n]; cos_prev_host float32 [n] (cos with the previous frame, [0] = 1) if non-NULL;
+ *            stats[0] = scenes that survived the length filter, stats[1] = frames inside them, if non-NULL. */
+IVR_API int ivr_frame_filter(int device, const float* e_host, int64_t n, int d, int window, float thr,
+                     float transition_thr, int min_scene_len, uint8_t* keep_host, float* cos_prev_host,
+                     int64_t stats[2]);
+
 /* Timing of the last ivr_dedup_window_device call on this thread (events on the
  * launching stream): ms[0] = banded-cosine kernel, ms[1] = greedy resolve kernel. */
 IVR_API int ivr_dedup_set_timing(int enable);

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "ivr_dedup_window_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ivr_frame_filter": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "ivr_dedup_set_timing": (C.c_int, [C.c_int]),
     "ivr_dedup_last_timing": (C.c_int, [_c_f32p]),
     "ivr_dedup_chain": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

@@ -45,8 +45,10 @@ int reconstruct_rows(ivr_index* idx, int64_t first, int64_t n, float* dst_dev, c
 int pack_parts(const float* D, const int64_t* I, uint64_t* keys, int64_t n, cudaStream_t st);
 int dedup_set_timing(int enable);
 int dedup_last_timing(float ms[2]);
-int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, uint32_t* masks,
+int launch_banded(const float* e_dev, int64_t n, int64_t out_begin, int d, int window, float thr, uint32_t* masks,
                   float* cos_prev, int sm_count, cudaStream_t st);
+int launch_scene_resolve(const uint32_t* masks, const float* cos_prev, int64_t n, int window, float transition_thr,
+                         int min_len, uint8_t* keep, unsigned long long* stats, cudaStream_t st);
 int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
                         const int64_t* scene_start_dev, const int64_t* scene_end_dev,
                         int64_t n_scenes, int window, float thr, uint8_t* keep_dev,
@@ -83,15 +85,30 @@ static int require_device(int device) {
         return IVR_ENODEVICE;
     }
     IVR_CUDA(cudaSetDevice(device));
+    static bool pool_kept[64] = {};
+    if (device < 64 && !pool_kept[device]) {                        // keep freed blocks in the pool (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t never = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+        }
+        cudaGetLastError();
+        pool_kept[device] = true;
+    }
     return IVR_OK;
 }
 
-// scoped device buffer for the host-pointer dedup / normalise entry points
+// Scoped device buffer for the host-pointer dedup / normalise entry points.  Stream-ordered allocation from the
+// device's default memory pool, whose release threshold require_device() raises to "never": after the first call
+// the blocks come back from the pool without a driver allocation (a cudaMalloc / cudaFree pair per call used to cost
+// more than the kernels they served).
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        IVR_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes, cudaStream_t stream = nullptr) {
+        st = stream;
+        IVR_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
         return IVR_OK;
     }
 };
@@ -317,8 +334,13 @@ namespace ivr {
 // shapes neither tcgen05 kernel fits (e.g. dim > 1024 with a large batch) stream.
 static int choose_path(const ivr_index* idx, int64_t nq, int k, int path) {
     const bool small_ok = mma_small_supported(idx, nq, k), big_ok = mma_supported(idx, nq, k);
-    if (path == IVR_PATH_AUTO)
+    if (path == IVR_PATH_AUTO) {
+        // tuning knob (measurements only): largest batch the streaming kernel serves in automatic mode
+        const char* e = getenv("IVR_AUTO_STREAM_MAX_NQ");
+        const int64_t stream_max = (e && *e) ? atoi(e) : 1;
+        if (nq <= stream_max) return IVR_PATH_STREAM;
         return ((nq >= 2 && small_ok) || (nq > 2 && big_ok)) ? IVR_PATH_MMA : IVR_PATH_STREAM;
+    }
     if (path == IVR_PATH_MMA && !small_ok && !big_ok) {
         set_error("search: the tcgen05 path does not support dim=%d nq=%lld k=%d", idx->dim,
                   static_cast<long long>(nq), k);
@@ -525,7 +547,7 @@ int ivr_consecutive_cosine_device(int device, const float* e_dev, int64_t n, int
     IVR_TRY(require_device(device));
     int sm = 0;
     IVR_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
-    return launch_banded(e_dev, n, d, 1, 2.0f, nullptr, out_dev, sm, static_cast<cudaStream_t>(stream));
+    return launch_banded(e_dev, n, 0, d, 1, 2.0f, nullptr, out_dev, sm, static_cast<cudaStream_t>(stream));
 }
 
 int ivr_consecutive_cosine(int device, const float* e_host, int64_t n, int d, float* out_host) {
@@ -558,6 +580,96 @@ int ivr_dedup_window_device(int device, const float* e_dev, int64_t n, int d,
     IVR_TRY(require_device(device));
     return dedup_window_device(device, e_dev, n, d, scene_start_dev, scene_end_dev, n_scenes, window,
                                thr, keep_dev, cos_prev_dev, mask_ws_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ivr_frame_filter(int device, const float* e_host, int64_t n, int d, int window, float thr, float transition_thr,
+                     int min_scene_len, uint8_t* keep_host, float* cos_prev_host, int64_t* stats) {
+    if (n < 0 || d <= 0 || (n > 0 && (!e_host || !keep_host))) { set_error("frame_filter: bad argument"); return IVR_EINVAL; }
+    if (window > IVR_MAX_WINDOW) {
+        set_error("frame_filter: window %d above %d", window, IVR_MAX_WINDOW);
+        return IVR_EUNSUPPORTED;
+    }
+    if (stats) stats[0] = stats[1] = 0;
+    if (n == 0) return IVR_OK;
+    IVR_TRY(require_device(device));
+    int sm = 0;
+    IVR_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    static thread_local cudaStream_t st = nullptr;
+    static thread_local int st_device = -1;
+    if (st_device != device) {
+        if (st) cudaStreamDestroy(st);
+        IVR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        st_device = device;
+    }
+    const int w_kernel = window < 1 ? 1 : window;                     // masks of an empty window are never consulted
+    const int halo = w_kernel;
+    const size_t row_bytes = static_cast<size_t>(d) * sizeof(float);
+    int64_t chunk = std::max<int64_t>(halo + 1, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(row_bytes));
+    chunk = std::min(chunk, n);
+    // Is the caller's buffer page-locked?  Then the chunks are copied straight from it; otherwise they are staged
+    // through two pinned buffers filled by a few host threads while the previous chunk is on the wire.
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, e_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    DevBuf buf, masks, cosp, keep, cnt;
+    IVR_TRY(buf.alloc((chunk + halo) * row_bytes, st));
+    IVR_TRY(masks.alloc(n * sizeof(uint32_t), st)); IVR_TRY(cosp.alloc(n * sizeof(float), st));
+    IVR_TRY(keep.alloc(n, st)); IVR_TRY(cnt.alloc(16, st));
+    void* pin = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = IVR_OK;
+    if (!pinned) {
+        static thread_local void* tl_pin = nullptr;
+        static thread_local size_t tl_pin_bytes = 0;
+        if (tl_pin_bytes < 2 * chunk * row_bytes) {
+            if (tl_pin) cudaFreeHost(tl_pin);
+            tl_pin = nullptr; tl_pin_bytes = 0;
+            IVR_CUDA(cudaMallocHost(&tl_pin, 2 * chunk * row_bytes));
+            tl_pin_bytes = 2 * chunk * row_bytes;
+        }
+        pin = tl_pin;
+        for (auto& e : done) IVR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    float* dbuf = static_cast<float*>(buf.p);
+    IVR_CUDA(cudaMemsetAsync(cnt.p, 0, 16, st));
+    int64_t off = 0;
+    for (int it = 0; off < n && rc == IVR_OK; ++it) {
+        const int64_t m = std::min(chunk, n - off);
+        const int64_t ctx = std::min<int64_t>(halo, off);             // look-back frames kept from the previous chunk
+        const float* src = e_host + off * d;
+        if (!pinned) {
+            const int b = it & 1;
+            char* p = static_cast<char*>(pin) + b * chunk * row_bytes;
+            if (it >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = IVR_ECUDA; break; }
+            staged_memcpy(p, src, m * row_bytes);
+            src = reinterpret_cast<const float*>(p);
+        }
+        if (cudaMemcpyAsync(dbuf + halo * d, src, m * row_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = IVR_ECUDA; break; }
+        if (!pinned) cudaEventRecord(done[it & 1], st);
+        // buffer rows [halo - ctx, halo + m) hold frames [off - ctx, off + m); outputs go to frames [off, off + m)
+        rc = launch_banded(dbuf + (halo - ctx) * d, ctx + m, ctx, d, w_kernel, thr,
+                           static_cast<uint32_t*>(masks.p) + (off - ctx), static_cast<float*>(cosp.p) + (off - ctx), sm, st);
+        if (rc != IVR_OK) break;
+        if (off + m < n &&                                            // keep the last `halo` frames as the next chunk's context
+            cudaMemcpyAsync(dbuf + std::max<int64_t>(0, halo - m) * d, dbuf + std::max<int64_t>(halo, m) * d,
+                            std::min<int64_t>(halo, m) * row_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { rc = IVR_ECUDA; break; }
+        off += m;
+    }
+    if (rc == IVR_OK)
+        rc = launch_scene_resolve(static_cast<uint32_t*>(masks.p), static_cast<float*>(cosp.p), n, window, transition_thr,
+                                  min_scene_len, static_cast<uint8_t*>(keep.p), static_cast<unsigned long long*>(cnt.p), st);
+    unsigned long long scenes[2] = {0, 0};
+    if (rc == IVR_OK) {
+        cudaMemcpyAsync(keep_host, keep.p, n, cudaMemcpyDeviceToHost, st);
+        if (cos_prev_host) cudaMemcpyAsync(cos_prev_host, cosp.p, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(scenes, cnt.p, 16, cudaMemcpyDeviceToHost, st);
+    }
+    const cudaError_t e = cudaStreamSynchronize(st);
+    for (auto& ev : done) if (ev) cudaEventDestroy(ev);
+    if (rc == IVR_OK && e != cudaSuccess) { set_error("frame_filter: %s", cudaGetErrorString(e)); rc = IVR_ECUDA; }
+    if (rc == IVR_ECUDA && g_err[0] == 0) set_error("frame_filter: CUDA failure");
+    if (rc == IVR_OK && stats) { stats[0] = static_cast<int64_t>(scenes[0]); stats[1] = static_cast<int64_t>(scenes[1]); }
+    return rc;
 }
 
 int ivr_dedup_window(int device, const float* e_host, int64_t n, int d, const int64_t* scene_start,

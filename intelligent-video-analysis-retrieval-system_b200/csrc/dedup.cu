@@ -26,14 +26,16 @@ constexpr int kDedupThreads = kDedupWarps * 32;
 // DV > 0: d == DV*128, each lane holds DV float4 of its row.  DV == 0: generic d.
 template <int DV>
 __global__ void __launch_bounds__(kDedupThreads)
-banded_cosine_kernel(const float* __restrict__ e, int64_t n, int d, int window, float thr,
+banded_cosine_kernel(const float* __restrict__ e, int64_t n, int64_t out_begin, int d, int window, float thr,
                      uint32_t* __restrict__ masks, float* __restrict__ cos_prev, int ring) {
     extern __shared__ float s_ring[];          // ring * dstride floats
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int dstride = (DV > 0) ? DV * 128 : ((d + 3) / 4 * 4);
 
-    // contiguous chunk of frames per CTA (+ a halo of `window` frames re-normalised locally)
-    const int64_t f0 = n * blockIdx.x / gridDim.x, f1 = n * (blockIdx.x + 1) / gridDim.x;
+    // contiguous chunk of the output frames [out_begin, n) per CTA (+ a halo of `window` frames re-normalised
+    // locally; frames before out_begin are context only -- the chunked host path re-uses the tail of the last chunk)
+    const int64_t span = n - out_begin;
+    const int64_t f0 = out_begin + span * blockIdx.x / gridDim.x, f1 = out_begin + span * (blockIdx.x + 1) / gridDim.x;
     if (f0 >= f1) return;
     const int64_t fs = (f0 - window > 0) ? f0 - window : 0;
 
@@ -119,131 +121,6 @@ banded_cosine_kernel(const float* __restrict__ e, int64_t n, int d, int window, 
 }
 
 // ---------------------------------------------------------------------------
-// Register-tiled variant for window <= 8 and d in {384, 512}: a warp owns FOUR consecutive frames,
-// so a parked row read from shared memory is reused by up to four dot products (11 row reads per
-// 32 dots instead of 32), and the 32 partial sums of a group are reduced with one 31-shuffle
-// transpose-reduction that leaves dot (frame g, offset dd) in lane 8*g + dd - 1.
-// ---------------------------------------------------------------------------
-constexpr int kG = 4;                           // frames per warp per batch
-constexpr int kG4Warps = 4;
-constexpr int kG4Batch = kG * kG4Warps;         // 16 frames per batch
-constexpr int kG4Window = 8;                    // offsets computed per frame
-constexpr int kG4Ring = kG4Window + 2 * kG4Batch;
-
-template <int DV>
-__global__ void __launch_bounds__(kG4Warps * 32, 2)
-banded_cosine_g4_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
-                        uint32_t* __restrict__ masks, float* __restrict__ cos_prev) {
-    extern __shared__ float s_ring[];          // kG4Ring rows of DV*128 floats
-    constexpr int RS = DV * 128;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t f0 = n * blockIdx.x / gridDim.x, f1 = n * (blockIdx.x + 1) / gridDim.x;
-    if (f0 >= f1) return;
-    const int64_t fs = (f0 - kG4Window > 0) ? f0 - kG4Window : 0;
-
-    float4 cur[kG][DV], nxt[kG][DV];
-    auto load_group = [&](int64_t i0, float4 (&r)[kG][DV]) {
-#pragma unroll
-        for (int g = 0; g < kG; ++g) {
-            const int64_t i = i0 + g;
-            const float4* p = reinterpret_cast<const float4*>(e + (i < f1 ? i : f1 - 1) * RS);
-#pragma unroll
-            for (int j = 0; j < DV; ++j) r[g][j] = ldg_nc_f4(p + lane + 32 * j);
-        }
-    };
-    int64_t base = fs;
-    load_group(base + warp * kG, nxt);
-
-    for (; base < f1; base += kG4Batch) {
-        const int64_t i0 = base + warp * kG;
-#pragma unroll
-        for (int g = 0; g < kG; ++g)
-#pragma unroll
-            for (int j = 0; j < DV; ++j) cur[g][j] = nxt[g][j];
-        if (base + kG4Batch < f1) load_group(i0 + kG4Batch, nxt);          // prefetch the next batch
-
-        // normalise the four rows (sklearn order: x / ||x||, zero norm -> 1) and park them
-        float ss[kG];
-#pragma unroll
-        for (int g = 0; g < kG; ++g) {
-            float a = 0.f;
-#pragma unroll
-            for (int j = 0; j < DV; ++j) {
-                a = fmaf(cur[g][j].x, cur[g][j].x, a); a = fmaf(cur[g][j].y, cur[g][j].y, a);
-                a = fmaf(cur[g][j].z, cur[g][j].z, a); a = fmaf(cur[g][j].w, cur[g][j].w, a);
-            }
-            ss[g] = a;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int g = 0; g < kG; ++g) ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
-#pragma unroll
-        for (int g = 0; g < kG; ++g) {
-            float nrm = sqrtf(ss[g]);
-            if (nrm == 0.f) nrm = 1.f;
-            const float inv = 1.0f / nrm;
-            float4* slot = reinterpret_cast<float4*>(s_ring + static_cast<size_t>((i0 + g) % kG4Ring) * RS);
-#pragma unroll
-            for (int j = 0; j < DV; ++j) {
-                cur[g][j].x *= inv; cur[g][j].y *= inv; cur[g][j].z *= inv; cur[g][j].w *= inv;
-                if (i0 + g < f1) slot[lane + 32 * j] = cur[g][j];
-            }
-        }
-        __syncthreads();
-
-        if (i0 < f1 && i0 + kG > f0) {                                      // warp-uniform: some live frame
-            float acc[kG * kG4Window];
-#pragma unroll
-            for (int a = 0; a < kG * kG4Window; ++a) acc[a] = 0.f;
-#pragma unroll
-            for (int rr = 0; rr < kG4Window + kG - 1; ++rr) {
-                const int64_t r = i0 - kG4Window + rr;
-                if (r < 0) continue;                                        // warp-uniform
-                const float4* other = reinterpret_cast<const float4*>(s_ring + static_cast<size_t>(r % kG4Ring) * RS);
-                float4 o[DV];
-#pragma unroll
-                for (int j = 0; j < DV; ++j) o[j] = other[lane + 32 * j];
-#pragma unroll
-                for (int g = 0; g < kG; ++g) {
-                    const int dd = kG4Window + g - rr;                      // frame i0+g minus row r
-                    if (dd >= 1 && dd <= kG4Window) {
-                        float a = acc[g * kG4Window + dd - 1];
-#pragma unroll
-                        for (int j = 0; j < DV; ++j) {
-                            a = fmaf(cur[g][j].x, o[j].x, a); a = fmaf(cur[g][j].y, o[j].y, a);
-                            a = fmaf(cur[g][j].z, o[j].z, a); a = fmaf(cur[g][j].w, o[j].w, a);
-                        }
-                        acc[g * kG4Window + dd - 1] = a;
-                    }
-                }
-            }
-            // transpose-reduce: after the 5 steps lane l holds the full sum of acc index l
-#pragma unroll
-            for (int s = 16, half = 16; s > 0; s >>= 1, half >>= 1) {
-                const bool up = (lane & s) != 0;
-#pragma unroll
-                for (int a = 0; a < half; ++a) {
-                    const float send = up ? acc[a] : acc[a + half];
-                    const float keep = up ? acc[a + half] : acc[a];
-                    acc[a] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                }
-            }
-            const float val = acc[0];
-            const int g = lane >> 3, dd = (lane & 7) + 1;
-            const int64_t i = i0 + g, j = i - dd;
-            const bool live = i >= f0 && i < f1;
-            const bool ge = live && dd <= window && j >= 0 && val >= thr;
-            const unsigned ballot = __ballot_sync(0xffffffffu, ge);
-            if (live && dd == 1) {
-                if (masks) masks[i] = (ballot >> (8 * g)) & 0xffu;
-                if (cos_prev) cos_prev[i] = (j >= 0) ? val : 1.0f;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // Register-window variant (window <= 8, d in {384, 512}) -- the default for those shapes.
 // Every WARP walks its own contiguous run of frames sequentially and keeps the last 8 normalised
 // rows in REGISTERS (the frame loop is unrolled by 8, so the window slot of a frame is a
@@ -281,28 +158,37 @@ __device__ __forceinline__ void fmul2(float& c0, float& c1, float a0, float a1, 
 
 template <int DV>
 __global__ void __launch_bounds__(kRwWarps * 32, 3)
-banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, float thr,
+banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int64_t out_begin, int window, float thr,
                         uint32_t* __restrict__ masks, float* __restrict__ cos_prev) {
     extern __shared__ float4 s_stage[];         // [kRwWarps][kRwSlots][DV * 32]
     constexpr int RS4 = DV * 32;                // float4 per row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kRwWarps + warp;
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kRwWarps;
-    const int64_t f0 = n * gw / nw, f1 = n * (gw + 1) / nw;
+    const int64_t span = n - out_begin;         // frames before out_begin are context only (chunked host path)
+    const int64_t f0 = out_begin + span * gw / nw, f1 = out_begin + span * (gw + 1) / nw;
     if (f0 >= f1) return;                        // no CTA-wide barrier anywhere below
     const int64_t fs = (f0 - kRwWindow > 0) ? f0 - kRwWindow : 0;
-    float4* stage = s_stage + static_cast<size_t>(warp) * kRwSlots * RS4;
-    const float4* src = reinterpret_cast<const float4*>(e);
+    // everything inside the frame loop is 32-bit and relative to fs (the kernel is bound by instruction issue)
+    const int total = static_cast<int>(f1 - fs);                     // frames this warp walks, halo included
+    const int first_out = static_cast<int>(f0 - fs);                 // first local frame that produces output
+    const int before = static_cast<int>(fs < kRwWindow ? fs : kRwWindow);   // real predecessors of local frame 0, capped
+    float4* const stage = s_stage + static_cast<size_t>(warp) * kRwSlots * RS4 + lane;   // this lane's column of the ring
+    const float4* pf = reinterpret_cast<const float4*>(e) + fs * RS4 + lane;             // next frame to prefetch
+    uint32_t* const mout = masks ? masks + fs : nullptr;
+    float* const cout = cos_prev ? cos_prev + fs : nullptr;
+    const int dd = (lane & 7) + 1;                                   // the look-back this lane reports (lanes 0..7 count)
 
-    auto issue = [&](int64_t i, int slot) {
-        if (i < f1) {
+    auto issue = [&](int t, int slot) {
+        if (t < total) {
 #pragma unroll
-            for (int j = 0; j < DV; ++j) cp_async16(stage + slot * RS4 + lane + 32 * j, src + i * RS4 + lane + 32 * j);
+            for (int j = 0; j < DV; ++j) cp_async16(stage + slot * RS4 + 32 * j, pf + 32 * j);
         }
+        pf += RS4;
         cp_async_commit();                      // always commit: keeps the group count uniform
     };
 #pragma unroll
-    for (int x = 0; x < kRwSlots - 1; ++x) issue(fs + x, x);
+    for (int x = 0; x < kRwSlots - 1; ++x) issue(x, x);
 
     float4 win[kRwWindow][DV];
 #pragma unroll
@@ -310,16 +196,16 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
 #pragma unroll
         for (int j = 0; j < DV; ++j) win[w][j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int64_t i = fs; i < f1; i += kRwWindow) {
+    for (int t0 = 0; t0 < total; t0 += kRwWindow) {
 #pragma unroll
         for (int u = 0; u < kRwWindow; ++u) {
-            const int64_t ii = i + u;
-            if (ii < f1) {                                                  // warp-uniform
-                cp_async_wait<kRwSlots - 2>();                              // frame ii has landed
+            const int t = t0 + u;
+            if (t < total) {                                                // warp-uniform
+                cp_async_wait<kRwSlots - 2>();                              // frame t has landed
                 float4 cur[DV];
 #pragma unroll
-                for (int j = 0; j < DV; ++j) cur[j] = stage[u * RS4 + lane + 32 * j];
-                issue(ii + kRwSlots - 1, (u + kRwSlots - 1) % kRwSlots);   // refill the slot read one step ago
+                for (int j = 0; j < DV; ++j) cur[j] = stage[u * RS4 + 32 * j];
+                issue(t + kRwSlots - 1, (u + kRwSlots - 1) % kRwSlots);    // refill the slot read one step ago
                 // The 8 dot products are taken with the RAW row and scaled by 1/||row|| afterwards
                 // (dot(x/|x|, w) == dot(x, w)/|x| up to one rounding), so the norm reduction and the
                 // dot reduction are two independent shuffle chains instead of one long one.
@@ -332,50 +218,49 @@ banded_cosine_rw_kernel(const float* __restrict__ e, int64_t n, int window, floa
                 float ss = ss0 + ss1;
                 float acc[kRwWindow];
 #pragma unroll
-                for (int dd = 1; dd <= kRwWindow; ++dd) {
-                    const int w = (u - dd + 2 * kRwWindow) % kRwWindow;     // slot of frame ii - dd
+                for (int d1 = 1; d1 <= kRwWindow; ++d1) {
+                    const int w = (u - d1 + 2 * kRwWindow) % kRwWindow;     // slot of frame t - d1
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int j = 0; j < DV; ++j) {
                         ffma2(a0, a1, cur[j].x, cur[j].y, win[w][j].x, win[w][j].y);
                         ffma2(a0, a1, cur[j].z, cur[j].w, win[w][j].z, win[w][j].w);
                     }
-                    acc[dd - 1] = a0 + a1;
+                    acc[d1 - 1] = a0 + a1;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                // transpose-reduce 8 sums over 32 lanes: lane l ends with the total of index l >> 2
+                // transpose-reduce the 8 sums: lane bit 2 picks index bit 2, bit 1 -> bit 1, bit 0 -> bit 0, so lane l
+                // ends with the partial of index l & 7; two more exchanges add the four 8-lane groups together
 #pragma unroll
-                for (int s = 16, half = 4; half > 0; s >>= 1, half >>= 1) {
-                    const bool up = (lane & s) != 0;
+                for (int s2 = 4, half = 4; half > 0; s2 >>= 1, half >>= 1) {
+                    const bool up = (lane & s2) != 0;
 #pragma unroll
                     for (int a = 0; a < half; ++a) {
                         const float send = up ? acc[a] : acc[a + half];
                         const float keep = up ? acc[a + half] : acc[a];
-                        acc[a] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                        acc[a] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
                     }
                 }
                 float val = acc[0];
-                val += __shfl_xor_sync(0xffffffffu, val, 2);
-                val += __shfl_xor_sync(0xffffffffu, val, 1);
-                float nrm = sqrtf(ss);
-                if (nrm == 0.f) nrm = 1.f;                                  // sklearn: 0 -> 1
-                const float inv = 1.0f / nrm;
+                val += __shfl_xor_sync(0xffffffffu, val, 8);
+                val += __shfl_xor_sync(0xffffffffu, val, 16);
+                // 1 / ||row||: reciprocal square root + one Newton step (within 2 ulp of 1 / sqrt(ss); no slow-path
+                // branches); sklearn divides by the norm and maps a zero norm to 1
+                float inv = rsqrtf(ss);
+                inv = inv * fmaf(-0.5f * ss, inv * inv, 1.5f);
+                if (ss == 0.f) inv = 1.f;
                 val *= inv;
 #pragma unroll
-                for (int j = 0; j < DV; ++j) {                              // frame ii (normalised) replaces frame ii - 8
+                for (int j = 0; j < DV; ++j) {                              // frame t (normalised) replaces frame t - 8
                     fmul2(win[u][j].x, win[u][j].y, cur[j].x, cur[j].y, inv, inv);
                     fmul2(win[u][j].z, win[u][j].w, cur[j].z, cur[j].w, inv, inv);
                 }
-                const int dd = (lane >> 2) + 1;
-                const bool ge = dd <= window && ii - dd >= 0 && val >= thr;
+                const bool ge = dd <= min(window, before + t) && val >= thr;   // only real predecessors inside the window
                 const unsigned ballot = __ballot_sync(0xffffffffu, ge);
-                if (ii >= f0 && lane == 0) {
-                    uint32_t m = 0;
-#pragma unroll
-                    for (int b = 0; b < kRwWindow; ++b) m |= ((ballot >> (4 * b)) & 1u) << b;
-                    if (masks) masks[ii] = m;
-                    if (cos_prev) cos_prev[ii] = (ii >= 1) ? val : 1.0f;
+                if (t >= first_out && lane == 0) {
+                    if (mout) mout[t] = ballot & 0xffu;                     // lanes 0..7 hold look-backs 1..8
+                    if (cout) cout[t] = (before + t >= 1) ? val : 1.0f;
                 }
             }
         }
@@ -401,6 +286,43 @@ __global__ void window_resolve_kernel(const uint32_t* __restrict__ masks,
         keep[i] = static_cast<uint8_t>(k);
         hist = (hist << 1) | k;                 // frames before the scene start are never set
     }
+}
+
+// Scene split AND greedy rule in one pass over the per-frame outputs of the banded kernel -- the device form of
+// detect_scene_transitions + group_into_scenes + filter_similar_frames_advanced per scene (filter.py:153-176, 224-315):
+// frame i starts a scene iff i == 0 or cos(e_i, e_{i-1}) < transition_thr (strict); a scene runs to the frame before
+// the next start; scenes shorter than min_len vanish (keep = 0); inside a scene the window rule runs on the masks.
+// One thread per frame; only scene-start threads do work (they walk their own scene: mean length ~20 frames).
+__global__ void scene_resolve_kernel(const uint32_t* __restrict__ masks, const float* __restrict__ cos_prev, int64_t n,
+                                     int window, float transition_thr, int min_len, uint8_t* __restrict__ keep,
+                                     unsigned long long* __restrict__ stats) {   // [scenes kept, frames inside them]
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    if (i != 0 && !(cos_prev[i] < transition_thr)) return;          // not a scene start
+    int64_t end = i + 1;
+    while (end < n && !(cos_prev[end] < transition_thr)) ++end;     // [i, end) is the scene
+    if (end - i < min_len) {
+        for (int64_t j = i; j < end; ++j) keep[j] = 0;
+        return;
+    }
+    if (stats) { atomicAdd(stats, 1ull); atomicAdd(stats + 1, static_cast<unsigned long long>(end - i)); }
+    const uint32_t wmask = (window >= 32) ? 0xffffffffu : ((1u << window) - 1u);
+    uint32_t hist = 0;                          // bit d-1 = keep flag of frame j-d (this scene only)
+    for (int64_t j = i; j < end; ++j) {
+        const uint32_t kf = (window <= 0 || (masks[j] & hist & wmask) == 0u) ? 1u : 0u;   // empty window keeps everything
+        keep[j] = static_cast<uint8_t>(kf);
+        hist = (hist << 1) | kf;
+    }
+}
+
+int launch_scene_resolve(const uint32_t* masks, const float* cos_prev, int64_t n, int window, float transition_thr,
+                         int min_len, uint8_t* keep, unsigned long long* stats, cudaStream_t st) {
+    if (n <= 0) return IVR_OK;
+    const int threads = 256;
+    scene_resolve_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, st>>>(
+        masks, cos_prev, n, window, transition_thr, min_len, keep, stats);
+    IVR_CUDA(cudaGetLastError());
+    return IVR_OK;
 }
 
 // One warp per scene: keep-chain rules with unbounded look-back in frame index.
@@ -487,45 +409,28 @@ static int env_flag(const char* name, int dflt) {
     return (e && *e) ? atoi(e) : dflt;
 }
 
-int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, uint32_t* masks,
+int launch_banded(const float* e_dev, int64_t n, int64_t out_begin, int d, int window, float thr, uint32_t* masks,
                   float* cos_prev, int sm_count, cudaStream_t st) {
-    if (n <= 0) return IVR_OK;
+    // Masks / cosines are produced for frames [out_begin, n); frames before out_begin are look-back context only.
+    if (n <= out_begin) return IVR_OK;
+    const int64_t span = n - out_begin;
     const bool aligned = (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0;
-    // IVR_DEDUP_KERNEL: 0 = register-window kernel (default for window <= 8, d = 384/512),
-    //                   1 = shared-ring 4-frames-per-warp kernel, 2 = generic kernel
+    // IVR_DEDUP_KERNEL: 0 = register-window kernel (default for window <= 8, d = 384/512), 2 = generic kernel
     const int variant = env_flag("IVR_DEDUP_KERNEL", 0);
     if (aligned && window <= kRwWindow && (d == 512 || d == 384) && variant == 0) {
         const size_t smem = static_cast<size_t>(kRwWarps) * kRwSlots * d * sizeof(float);
         int64_t grid = static_cast<int64_t>(sm_count) * 3;                  // persistent: 3 CTAs per SM
-        const int64_t max_grid = (n + 255) / 256;
+        const int64_t max_grid = (span + 255) / 256;
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
         if (d == 512) {
             auto kern = banded_cosine_rw_kernel<4>;
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, out_begin, window, thr, masks, cos_prev);
         } else {
             auto kern = banded_cosine_rw_kernel<3>;
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
-        }
-        IVR_CUDA(cudaGetLastError());
-        return IVR_OK;
-    }
-    if (aligned && window <= kG4Window && (d == 512 || d == 384) && variant == 1) {
-        const size_t smem = static_cast<size_t>(kG4Ring) * d * sizeof(float);
-        int64_t grid = static_cast<int64_t>(sm_count) * 4;
-        const int64_t max_grid = (n + 127) / 128;
-        if (grid > max_grid) grid = max_grid;
-        if (grid < 1) grid = 1;
-        if (d == 512) {
-            auto kern = banded_cosine_g4_kernel<4>;
-            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<static_cast<unsigned>(grid), kG4Warps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
-        } else {
-            auto kern = banded_cosine_g4_kernel<3>;
-            IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<static_cast<unsigned>(grid), kG4Warps * 32, smem, st>>>(e_dev, n, window, thr, masks, cos_prev);
+            kern<<<static_cast<unsigned>(grid), kRwWarps * 32, smem, st>>>(e_dev, n, out_begin, window, thr, masks, cos_prev);
         }
         IVR_CUDA(cudaGetLastError());
         return IVR_OK;
@@ -542,7 +447,7 @@ int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, u
     // enough CTAs to fill the machine twice over, but chunks of at least 64 frames so the
     // re-normalised halo stays a small fraction of the work
     int64_t grid = static_cast<int64_t>(sm_count) * 4;
-    const int64_t max_grid = (n + 63) / 64;
+    const int64_t max_grid = (span + 63) / 64;
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
 #define IVR_LAUNCH_BANDED(DV)                                                                      \
@@ -551,7 +456,7 @@ int launch_banded(const float* e_dev, int64_t n, int d, int window, float thr, u
         if (smem > 48 * 1024)                                                                      \
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                           static_cast<int>(smem)));                                \
-        kern<<<static_cast<unsigned>(grid), kDedupThreads, smem, st>>>(e_dev, n, d, window, thr,   \
+        kern<<<static_cast<unsigned>(grid), kDedupThreads, smem, st>>>(e_dev, n, out_begin, d, window, thr,  \
                                                                        masks, cos_prev, ring);     \
     } while (0)
     switch (dv) {
@@ -576,7 +481,7 @@ int dedup_window_device(int device, const float* e_dev, int64_t n, int d,
     if (g_dedup_timing && !g_dedup_ev[0])
         for (auto& ev : g_dedup_ev) IVR_CUDA(cudaEventCreate(&ev));
     if (g_dedup_timing) cudaEventRecord(g_dedup_ev[0], st);
-    IVR_TRY(launch_banded(e_dev, n, d, window, thr, mask_ws_dev, cos_prev_dev, sm_count, st));
+    IVR_TRY(launch_banded(e_dev, n, 0, d, window, thr, mask_ws_dev, cos_prev_dev, sm_count, st));
     if (g_dedup_timing) { cudaEventRecord(g_dedup_ev[1], st); cudaEventRecord(g_dedup_ev[2], st); }
     IVR_CUDA(cudaMemsetAsync(keep_dev, 0, static_cast<size_t>(n), st));
     if (n_scenes > 0) {

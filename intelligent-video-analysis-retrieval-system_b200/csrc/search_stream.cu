@@ -4,10 +4,16 @@
 // call is nq = 1: unified_index.py:503).  The fp16 row matrix is streamed once
 // with 128-bit coalesced, L1-bypassing loads; every 8 lanes own one row, so a
 // warp covers 4 rows per step and keeps 2 steps (8 rows) of loads in flight.
+// The 8-row groups are dealt to the warps ROUND-ROBIN (group g -> warp g mod W):
+// at any moment the grid reads one contiguous window of the matrix, and -- what
+// the merge relies on -- neighbouring rows (near-duplicate frames of one video)
+// end up in different warps' lists.
 // Scores are reduced with 3 shuffles and go straight into a per-warp candidate
 // list guarded by a running admission threshold (the warp's current k-th best);
 // full lists are compacted in registers (warp bitonic sort).  No score ever
-// reaches HBM; the per-warp survivors are folded by topk_merge.cu.
+// reaches HBM.  Every warp also publishes the MAXIMUM score of its list: the
+// k-th largest of those maxima bounds the final k-th best from below, which lets
+// topk_merge.cu fold the 2368 lists in ONE launch (merge_select_kernel).
 //
 // Algorithmic HBM traffic: ntotal * dpad * 2 bytes per pass.
 #include "index.cuh"
@@ -25,7 +31,8 @@ template <int NQ, int DCH, int E>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
                      const float* __restrict__ q,      // [NQ, dpad] fp32
-                     int k, int C, uint64_t* __restrict__ lists, int* __restrict__ counts) {
+                     int k, int C, uint64_t* __restrict__ lists, int* __restrict__ counts,
+                     uint32_t* __restrict__ maxima) {
     extern __shared__ float s_q[];                     // NQ * dpad
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rgrp = lane >> 3;
@@ -36,9 +43,9 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
 
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kStreamWarps + warp;
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kStreamWarps;
-    // contiguous, 4-row aligned slab per warp
+    // groups of kUnroll steps (8 rows) dealt round-robin to the warps of the grid
     const int64_t steps_total = (n_rows + kRowsPerStep - 1) / kRowsPerStep;
-    const int64_t s0 = steps_total * gw / nw, s1 = steps_total * (gw + 1) / nw;
+    const int64_t s1 = steps_total;
 
     uint64_t* my_lists = lists + gw * NQ * C;
     int   cnt[NQ];
@@ -46,7 +53,7 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
 #pragma unroll
     for (int i = 0; i < NQ; ++i) { cnt[i] = 0; tau[i] = __int_as_float(0xff800000); }
 
-    for (int64_t s = s0; s < s1; s += kUnroll) {
+    for (int64_t s = gw * kUnroll; s < s1; s += nw * kUnroll) {
         float acc[kUnroll][NQ];
         int64_t row[kUnroll];
         uint4 x[kUnroll][(DCH > 0) ? DCH : 1];
@@ -136,20 +143,20 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
             }
         }
     }
+    // the list is left as it is (up to C entries: the merge filters it); publish its size and its maximum score
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
-        if (cnt[i] > k) {
-            __syncwarp();
-            warp_compact<E>(my_lists + i * C, cnt[i], k, C, lane);
-            cnt[i] = k;
-        }
-        if (lane == 0) counts[gw * NQ + i] = cnt[i];
+        uint32_t mx = 0;
+        for (int j = lane; j < cnt[i]; j += 32) mx = max(mx, static_cast<uint32_t>(my_lists[i * C + j] >> 32));
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) { counts[gw * NQ + i] = cnt[i]; maxima[gw * NQ + i] = mx; }
     }
 }
 
 template <int NQ, int E>
 static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint64_t* lists, int* counts,
-                         int grid, cudaStream_t st) {
+                         uint32_t* maxima, int grid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(NQ) * idx->dpad * sizeof(float);
     const int dch = idx->dpad / 64;
 #define IVR_LAUNCH_STREAM(DCH)                                                                     \
@@ -159,7 +166,7 @@ static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint6
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                           static_cast<int>(smem)));                                \
         kern<<<grid, kStreamThreads, smem, st>>>(idx->rows, idx->ntotal, idx->dpad, q_pad, k, C,   \
-                                                 lists, counts);                                   \
+                                                 lists, counts, maxima);                           \
     } while (0)
     switch (dch) {
         case 8:  IVR_LAUNCH_STREAM(8);  break;     // 512  (CLIP ViT-B/32)
@@ -173,18 +180,19 @@ static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint6
 
 template <int E>
 static int launch_stream_nq(ivr_index* idx, int nq, const float* q_pad, int k, int C, uint64_t* lists,
-                            int* counts, int grid, cudaStream_t st) {
+                            int* counts, uint32_t* maxima, int grid, cudaStream_t st) {
     switch (nq) {                                  // nq == 3 runs as 4 with a zero query
-        case 1: return launch_stream<1, E>(idx, q_pad, k, C, lists, counts, grid, st);
-        case 2: return launch_stream<2, E>(idx, q_pad, k, C, lists, counts, grid, st);
-        default: return launch_stream<4, E>(idx, q_pad, k, C, lists, counts, grid, st);
+        case 1: return launch_stream<1, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
+        case 2: return launch_stream<2, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
+        default: return launch_stream<4, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
     }
 }
 
-// fp32 [nq, dim] -> fp32 [nq, dpad] zero padded
+// fp32 [nq, dim] -> fp32 [nq, dpad] zero padded; also zeroes the merge's pool counters / tickets (2 * kStreamMaxNq ints)
 __global__ void pad_queries_kernel(const float* __restrict__ q, float* __restrict__ out,
-                                   int64_t nq_real, int64_t nq_out, int dim, int dpad) {
+                                   int64_t nq_real, int64_t nq_out, int dim, int dpad, int* __restrict__ merge_state) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i < 2 * kStreamMaxNq) merge_state[i] = 0;
     if (i >= nq_out * dpad) return;
     const int64_t r = i / dpad;
     const int c = static_cast<int>(i % dpad);
@@ -203,10 +211,12 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
     const size_t list_keys = static_cast<size_t>(n_lists) * kStreamMaxNq * C;
     const size_t tmp_keys = merge_tmp_entries(static_cast<int>(n_lists), kStreamMaxNq, k);
     const size_t cnt_ints = static_cast<size_t>(n_lists) * kStreamMaxNq * 2 + 1024;
+    const bool select = k <= kSelectMaxK;             // one-launch merge by the list-maxima bound; exact radix levels above
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_q = carve(q_bytes), o_l = carve(list_keys * 8), o_t = carve(tmp_keys * 8),
-                 o_c = carve(cnt_ints * 4);
+                 o_c = carve(cnt_ints * 4), o_m = carve(static_cast<size_t>(n_lists) * kStreamMaxNq * 4),
+                 o_p = carve(static_cast<size_t>(kStreamMaxNq) * kSelectPoolCap * 8), o_s = carve(2 * kStreamMaxNq * 4);
     IVR_TRY(ensure_ws(idx, off));
     char* ws = static_cast<char*>(idx->ws);
     float* q_pad = reinterpret_cast<float*>(ws + o_q);
@@ -214,6 +224,9 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
     uint64_t* tmp = reinterpret_cast<uint64_t*>(ws + o_t);
     int* counts = reinterpret_cast<int*>(ws + o_c);
     int* tmp_counts = counts + n_lists * kStreamMaxNq;
+    uint32_t* maxima = reinterpret_cast<uint32_t*>(ws + o_m);
+    uint64_t* pool = reinterpret_cast<uint64_t*>(ws + o_p);
+    int* merge_state = reinterpret_cast<int*>(ws + o_s);      // [kStreamMaxNq] pool counters, [kStreamMaxNq] tickets
 
     for (int64_t q0 = 0; q0 < nq; q0 += kStreamMaxNq) {
         const int b_real = static_cast<int>(nq - q0 < kStreamMaxNq ? nq - q0 : kStreamMaxNq);
@@ -222,15 +235,15 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
         {
             const int64_t n = static_cast<int64_t>(b) * idx->dpad;
             pad_queries_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-                q_dev + q0 * idx->dim, q_pad, b_real, b, idx->dim, idx->dpad);
+                q_dev + q0 * idx->dim, q_pad, b_real, b, idx->dim, idx->dpad, merge_state);
             IVR_CUDA(cudaGetLastError());
             idx->launches[2]++;
         }
         if (idx->timing && q0 == 0) { cudaEventRecord(idx->ev[5], st); cudaEventRecord(idx->ev[0], st); }
         int rc;
         switch (kcap) {
-            case 128: rc = launch_stream_nq<8>(idx, b, q_pad, k, C, lists, counts, grid, st); break;   // k <= 128: register sort
-            default:  rc = launch_stream_nq<0>(idx, b, q_pad, k, C, lists, counts, grid, st); break;   // larger k: in-memory sort
+            case 128: rc = launch_stream_nq<8>(idx, b, q_pad, k, C, lists, counts, maxima, grid, st); break;   // k <= 128: register sort
+            default:  rc = launch_stream_nq<0>(idx, b, q_pad, k, C, lists, counts, maxima, grid, st); break;   // larger k: in-memory sort
         }
         IVR_TRY(rc);
         idx->launches[0]++;
@@ -240,8 +253,12 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
         in.list_stride = static_cast<int64_t>(b) * C; in.q_stride = C;
         in.cnt_list_stride = b; in.cnt_q_stride = 1;
         in.n_lists = static_cast<int>(n_lists); in.fixed_count = 0;
-        IVR_TRY(merge_lists_final(in, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset, tmp,
-                                  tmp_counts, st, &idx->launches[1]));
+        if (select)
+            IVR_TRY(merge_select_final(in, maxima, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset,
+                                       pool, merge_state, merge_state + kStreamMaxNq, idx->sm_count, st, &idx->launches[1]));
+        else
+            IVR_TRY(merge_lists_final(in, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset, tmp,
+                                      tmp_counts, st, &idx->launches[1]));
         if (idx->timing && q0 == 0) cudaEventRecord(idx->ev[3], st);
     }
     if (idx->timing) idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;

@@ -316,14 +316,32 @@ class FrameFilter:
         self.last_stats: Dict = {}
 
     def apply_filters(self, embeddings, window: int | None = None, threshold: float | None = None) -> np.ndarray:
+        """Kept frame indices (ascending int64).  ONE C call (``ivr_frame_filter``): the frames cross PCIe once, in
+        chunks whose banded-cosine kernels are queued behind their copies; the scene split and the greedy rule run on
+        the device too.  Pass a page-locked array (e.g. ``torch.empty(...).pin_memory().numpy()``) to skip the staging
+        copy.  Windows above ``IVR_MAX_WINDOW`` fall back to the scene-list entry point (it clamps the window to the
+        longest scene first, as the reference's ``min(window, len(scene))`` does)."""
         window = self.window if window is None else int(window)
         threshold = self.threshold if threshold is None else float(threshold)
         x, _ = _as_matrix(embeddings)
         n = x.shape[0]
         if n == 0:
             return np.zeros(0, np.int64)
-        # pass 1 gives the consecutive cosine (scene cuts); the masks of the same pass are
-        # resolved per scene in pass 2's tiny greedy kernel
+        if window > nat.IVR_MAX_WINDOW:
+            return self._apply_filters_scene_list(x, window, threshold)
+        keep = np.empty(n, np.uint8)
+        stats = (C.c_int64 * 2)()
+        nat.check(nat.lib.ivr_frame_filter(
+            nat.default_device() if self.device is None else self.device, x.ctypes.data, n, x.shape[1], window,
+            C.c_float(threshold), C.c_float(self.transition_threshold), self.min_scene_length,
+            keep.ctypes.data, None, stats))
+        kept = np.flatnonzero(keep).astype(np.int64)
+        self.last_stats = {"original": int(stats[1]), "filtered": int(kept.size), "removed": int(stats[1]) - int(kept.size),
+                           "scenes": int(stats[0])}
+        return kept
+
+    def _apply_filters_scene_list(self, x: np.ndarray, window: int, threshold: float) -> np.ndarray:
+        n = x.shape[0]
         sims = np.empty(max(n - 1, 0), np.float32)
         if n > 1:
             nat.check(nat.lib.ivr_consecutive_cosine(
@@ -335,12 +353,7 @@ class FrameFilter:
             self.last_stats = {"original": 0, "filtered": 0, "removed": 0, "scenes": 0}
             return np.zeros(0, np.int64)
         longest = max(e - s + 1 for s, e in scenes)
-        if window <= 0:                              # filter.py:233,242: an empty window keeps every frame of every scene
-            keep = np.zeros(n, np.uint8)
-            for s, e in scenes:
-                keep[s:e + 1] = 1
-        else:
-            keep, _ = _dedup_window(x, scenes, max(1, min(window, max(longest - 1, 1))), threshold, self.device)
+        keep, _ = _dedup_window(x, scenes, max(1, min(window, max(longest - 1, 1))), threshold, self.device)
         kept = np.nonzero(keep)[0].astype(np.int64)
         orig = int(sum(e - s + 1 for s, e in scenes))
         self.last_stats = {"original": orig, "filtered": int(kept.size), "removed": orig - int(kept.size),

@@ -211,3 +211,63 @@ def test_cluster_similar_frames_large_scene_vs_oracle():
     assert ff.cluster_similar_frames([x[0], x[0]]) == [[0, 1]]
     with pytest.raises(nat.NativeError):
         ff.cluster_similar_frames(np.zeros((8193, 4), np.float32))
+
+
+# ---------------------------------------------------------------------------
+# ivr_frame_filter: the whole similarity stage in one call (chunked H2D, device-side scene split + greedy rule)
+# ---------------------------------------------------------------------------
+def _want_keep(x, window, thr, transition, min_len):
+    sims = od.consecutive_cosines_fast(x)
+    scenes = od.scenes_from_cosines(sims, len(x), transition, min_len)
+    if window <= 0:
+        keep = np.zeros(len(x), np.uint8)
+        for s, e in scenes:
+            keep[s:e + 1] = 1
+        return keep, scenes
+    return od.window_keep_mask(x, scenes, window, thr), scenes
+
+
+@pytest.mark.parametrize("n,d,window,min_len", [
+    (100_001, 512, 8, 2),        # register-window kernel, 4 chunks of 32768 frames: look-back crosses chunk boundaries
+    (70_000, 384, 5, 1),         # DINO ViT-S/16 width, chunk = 43690 frames
+    (40_000, 512, 1, 2), (40_000, 512, 3, 5),
+    (600_000, 64, 8, 2),         # generic kernel, 3 chunks of 262144 frames
+    (9_000, 100, 12, 2),         # window > 8 -> generic kernel; unaligned dimension
+    (5_000, 512, 0, 2), (300, 512, 32, 2), (1, 512, 8, 1), (2, 64, 8, 2),
+])
+def test_frame_filter_single_call_matches_oracle(n, d, window, min_len):
+    import ctypes as C
+    from ivr_b200 import _native as nat, frame_filter as ff
+    thr, transition = 0.95, 0.75
+    x, _ = synth.dedup_frames_guarded(n, d, window=max(window, 1), thresholds=(thr, transition), seed=400 + d + window)
+    want, scenes = _want_keep(x, window, thr, transition, min_len)
+    keep = np.zeros(n, np.uint8)
+    cosp = np.zeros(n, np.float32)
+    stats = (C.c_int64 * 2)()
+    nat.check(nat.lib.ivr_frame_filter(0, x.ctypes.data, n, d, window, C.c_float(thr), C.c_float(transition), min_len,
+                                       keep.ctypes.data, cosp.ctypes.data, stats))
+    assert np.array_equal(keep, want), (int((keep != want).sum()), np.flatnonzero(keep != want)[:5])
+    assert stats[0] == len(scenes) and stats[1] == sum(e - s + 1 for s, e in scenes)
+    assert cosp[0] == 1.0
+    if n > 1:
+        np.testing.assert_allclose(cosp[1:], od.consecutive_cosines_fast(x), rtol=0, atol=2e-6)
+    # the facade, pageable and page-locked input, and the scene-list entry point agree
+    f = ff.FrameFilter(window=window, threshold=thr, transition_threshold=transition, min_scene_length=min_len)
+    kept = f.apply_filters(x)
+    assert np.array_equal(kept, np.flatnonzero(want)) and f.last_stats["scenes"] == len(scenes)
+    import torch
+    xp = torch.from_numpy(x).pin_memory()
+    assert np.array_equal(f.apply_filters(xp.numpy()), kept)
+    if 0 < window:
+        assert np.array_equal(f._apply_filters_scene_list(x, window, thr), kept)
+
+
+def test_frame_filter_window_above_the_mask_width_uses_the_scene_list_path():
+    from ivr_b200 import frame_filter as ff
+    x, _ = synth.dedup_frames_guarded(3000, 64, window=8, thresholds=(0.95, 0.75), seed=77)
+    want, _ = _want_keep(x, 40, 0.95, 0.75, 2)                     # scenes are far shorter than 32 frames here? not all
+    longest = max(e - s + 1 for s, e in od.scenes_from_cosines(od.consecutive_cosines_fast(x), len(x), 0.75, 2))
+    if longest - 1 > 32:
+        pytest.skip("a scene longer than the mask width: the reference semantics need window > 32 there")
+    kept = ff.FrameFilter(window=40, threshold=0.95).apply_filters(x)
+    assert np.array_equal(kept, np.flatnonzero(want))
