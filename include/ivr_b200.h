@@ -221,6 +221,21 @@ IVR_API int ivr_sequence_similarity(int device, const float* target_host, int64_
 #define IVR_MAX_CLUSTER_FRAMES 8192
 IVR_API int ivr_cosine_neighbors(int device, const float* e_host, int64_t n, int dim, float eps, uint32_t* adj_host);
 
+/* ------------------------------------------------------------------------
+ * .rvdb container: host-side block decoders
+ * The reference keeps its embeddings in an HDF5 dataset filtered with shuffle + LZF and its metadata / index
+ * blobs as LZ4 frames (unified_index.py:943-956, 1175-1234, 1827-1860).  rvdb_reader.py parses the container;
+ * these decode one chunk / block each (plain C on the host, no device involved).
+ * ---------------------------------------------------------------------- */
+/* liblzf stream -> bytes; returns the decoded size or -1 (malformed input / dst too small) */
+IVR_API int64_t ivr_lzf_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_cap);
+/* one LZ4 block, written at dst + dst_pos (matches may reach back into dst[0, dst_pos): linked blocks of a
+ * frame); returns the bytes produced or -1 */
+IVR_API int64_t ivr_lz4_block_decompress(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_pos,
+                                 int64_t dst_cap);
+/* inverse of the HDF5 shuffle filter (filter id 2) for elements of elem_size bytes */
+IVR_API int     ivr_unshuffle(const uint8_t* src, int64_t n_bytes, int elem_size, uint8_t* dst);
+
 #ifdef __cplusplus
 }
 #endif

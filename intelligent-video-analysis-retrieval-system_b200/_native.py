@@ -77,6 +77,9 @@ PROTOTYPES = {
                                           C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_int64)]),
     "ivr_cosine_neighbors": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "ivr_lzf_decompress": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "ivr_lz4_block_decompress": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "ivr_unshuffle": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
 }
 
 

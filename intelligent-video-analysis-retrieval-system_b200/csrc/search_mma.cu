@@ -106,7 +106,6 @@ struct MmaParams {
     int     nq_pad;          // tq * 128 * CG
     int     segs_max;        // max query tiles one group touches
     uint64_t row_policy;     // L2 eviction priority of the row-tile loads
-    int      prefetch;       // row tiles requested into L2 this many units ahead of their TMA loads (0 = off)
     int      skip_epilogue;  // debug/perf probe: drain nothing (results are garbage)
     uint64_t* lists;         // [slots][nq_pad / 32][C][32] raw candidate lists, interleaved per warp
     int*      counts;        // [slots][nq_pad]
@@ -226,18 +225,6 @@ search_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if (nload == 0) load_q();                              // very first tile: nothing to overlap
             },
             [&](int, int, int64_t j, int64_t) {
-                // With one or two query tiles every row tile comes straight from HBM, and the ring (6 x 16 KB per CTA
-                // beside a 128 KB query tile) holds too few bytes in flight to cover the HBM latency at full rate:
-                // ask L2 for the tile this group will need `prefetch` units from now.
-                if (p.prefetch > 0) {
-                    const int64_t jn = j + static_cast<int64_t>(p.prefetch) * (group < p.g_grid ? p.c : 1);
-                    if (jn < (group < p.g_grid ? p.ntg : p.nt))
-                        for (int kb = 0; kb < p.kblocks; ++kb)
-                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                                         ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(kb * kKBlock),
-                                           "r"(static_cast<int>((p.tile0 + jn) * kTileN) + static_cast<int>(cta_rank) * kRowsPerCta)
-                                         : "memory");
-                }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     if (pending_q && issued_since >= p.stages) load_q();
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -416,6 +403,7 @@ struct XresParams {
     int*      counts;        // [groups][2 sets][nq_pad]
     uint32_t* tau_g;         // [nq_pad] shared per-query threshold (order-preserving encoding)
     uint64_t  row_policy;
+    int       prefetch;        // pull the next row tile into L2 halfway through the current one
     int       skip_epilogue;   // debug/perf probe: drain nothing (results are garbage)
 };
 
@@ -476,7 +464,7 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             };
             if (nload == 0) load_x();
             for (int t = 0; t < p.tq; ++t) {
-                if (t == p.tq / 2 && j + 1 < j1) {
+                if (p.prefetch && t == p.tq / 2 && j + 1 < j1) {
                     // pull the next row tile into L2 while this one is being used
                     for (int kb = 0; kb < p.kblocks; ++kb)
                         asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
@@ -713,9 +701,6 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
     p.ntg = (p.g_grid == p.groups) ? p.nt : (p.nt * p.g_grid + p.groups / 2) / p.groups;
     if (p.nt - p.ntg > 0 && static_cast<int64_t>(p.tq) * (p.nt - p.ntg) < p.groups - p.g_grid) p.ntg = p.nt;
     p.stagger = std::max(0, env_int("IVR_MMA_STAGGER", 1));
-    // few query tiles => the rows stream from HBM (no L2 reuse across query tiles): prefetch ahead; with many query
-    // tiles the lockstep schedule already finds most row tiles in L2
-    p.prefetch = std::max(0, env_int("IVR_MMA_PREFETCH_UNITS", p.tq <= 2 ? 2 : 0));
 #ifdef IVR_PROBES
     p.skip_epilogue = env_int("IVR_MMA_DEBUG_SKIP_EPILOGUE", 0);
 #endif
@@ -776,6 +761,7 @@ static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int
         const int pol = env_int("IVR_MMA_ROW_POLICY", 1);          // rows are read once: evict-first by default
         p.row_policy = pol == 1 ? kL2EvictFirst : (pol == 2 ? kL2EvictLast : kL2EvictNormal);
     }
+    p.prefetch = env_int("IVR_XRES_PREFETCH", 1);
     p.tn = xres_tile_rows(idx);
     const int stage_bytes = kTileQ * 128;
     const int x_bytes = p.kblocks * (p.tn / cg) * 128;

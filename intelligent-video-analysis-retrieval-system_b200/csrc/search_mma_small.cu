@@ -52,7 +52,6 @@ struct SmallParams {
     int64_t nt;              // row tiles of this launch
     int64_t tile0;           // first row tile of this launch (row id = (tile0 + j) * 128 + lane)
     uint64_t row_policy;     // L2 eviction priority of the row loads
-    int      prefetch;       // row tiles requested into L2 this many tiles ahead of their TMA loads (0 = off)
     uint64_t* lists;         // [grid][4 warps][npad][C] raw candidate lists
     int*      counts;        // [grid][4 warps][npad]
     uint32_t* tau_g;         // [npad] shared per-query thresholds (order-preserving encoding)
@@ -116,11 +115,6 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         int stage = 0; uint32_t phase = 0;
         for (int64_t j = j0; j < j1; ++j) {
             const int row0 = static_cast<int>((p.tile0 + j) * kSmallTileRows);
-            if (p.prefetch > 0 && j + p.prefetch < j1)
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(kb * kKBlock),
-                                   "r"(row0 + p.prefetch * kSmallTileRows) : "memory");
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), kSmallStageBytes);
@@ -344,8 +338,6 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
         p.kblocks = idx->dpad / kKBlock; p.stages = sh.stages; p.nbuf = sh.nbuf; p.buf_cols = sh.buf_cols;
         p.tile0 = bounds[ph]; p.nt = bounds[ph + 1] - bounds[ph];
         p.row_policy = kL2EvictFirst;                                // every row is read exactly once
-        // wide query tiles leave a short row ring (5-9 stages): let L2 run ahead of it
-        p.prefetch = std::max(0, env_int("IVR_SMALL_PREFETCH_TILES", sh.stages < 12 ? 2 : 0));
         p.lists = reinterpret_cast<uint64_t*>(ws + o_l);
         p.counts = reinterpret_cast<int*>(ws + o_c);
         p.tau_g = tau_g;
