@@ -3,11 +3,11 @@
 Mirrors the search-side surface of the reference's ``unified_index.UnifiedIndex``
 (unified_index.py:63-92, 480-538, 638-673, 1449-1459, 1755-1793, 1889-1938) with
 the arithmetic moved to the sm_100a kernels behind ``faiss_compat.IndexFlatIP``.
-The .rvdb container I/O (HDF5 + LZ4 + JPEG thumbnails) is out of scope
-(SURVEY.md section 8f); an index is loaded from an in-memory embedding matrix and
-metadata list instead (``load_from_arrays`` / ``build_from_embeddings``), which is
-exactly what the reference holds after ``_setup_memory_maps`` (``self.vectors``,
-``self.metadata_list``, ``self.faiss_index``).
+An index is loaded either from an in-memory embedding matrix and metadata list
+(``load_from_arrays`` / ``build_from_embeddings``) -- what the reference holds after
+``_setup_memory_maps`` (``self.vectors``, ``self.metadata_list``, ``self.faiss_index``) --
+or from a ``.rvdb`` file (``load_unified_index``, via ``rvdb_reader``: the vector, index
+and metadata datasets only; thumbnails / images / checkpoints stay out of scope).
 
 Result semantics reproduced on purpose:
 ``similarity_score = 1.0 - inner_product`` and ``rank`` is the 0-based position
@@ -136,23 +136,50 @@ class UnifiedIndex:
             progress_callback(100, "done")
         return stats
 
-    def load_unified_index(self, index_file: str) -> Dict[str, Any]:
-        """Reads ``vectors/embeddings`` + ``metadata/data`` of a .rvdb file when h5py and
-        lz4 are importable (unified_index.py:1175-1234); otherwise fails loudly."""
-        try:
-            import h5py
-            import lz4.frame
-        except ImportError as e:
-            raise ImportError("loading .rvdb files needs h5py and lz4 (not in this image); "
-                              "use load_from_arrays(embeddings, metadata_list)") from e
-        import json
+    def load_unified_index(self, index_file: str, load_vectors: bool = False) -> Dict[str, Any]:
+        """Load a ``.rvdb`` file the way ``_setup_memory_maps`` does (unified_index.py:1175-1234), without h5py / lz4
+        (``rvdb_reader``: HDF5 subset + LZ4 frame + LZF, bulk bytes decoded in C):
+
+        * the index: the ``faiss_index`` dataset (raw bytes of ``faiss.write_index``) goes through
+          ``faiss.deserialize_index`` exactly as in the reference (1182); older files keep it LZ4-framed under
+          ``index/faiss`` (1185-1188); a file without either is indexed from its embeddings like
+          ``_build_faiss_index_from_file`` (1755-1793: 10 000-row chunks, ``normalize_L2``, ``add``) -- the chunks are
+          decoded and uploaded one after the other, the matrix is never assembled on the host;
+        * the metadata list: ``metadata/data`` (LZ4 frame around JSON);
+        * ``self.vectors``: the reference reads ALL embeddings into RAM here; searching does not need them, so they are
+          read only on request (``load_vectors=True``)."""
+        from . import rvdb_reader
         t0 = time.time()
-        with h5py.File(index_file, "r") as f:
-            vec = f["vectors"]["embeddings"][:] if "embeddings" in f["vectors"] else f["vectors"][:]
-            raw = bytes(f["metadata"]["data"][:]) if "data" in f["metadata"] else bytes(f["metadata"][:])
-            meta = json.loads(lz4.frame.decompress(raw).decode("utf-8"))
-        self.build_from_embeddings(vec, meta)
-        return {"load_time": time.time() - t0, "index_info": {"processed_files": len(meta)}}
+        r = rvdb_reader.read_rvdb(index_file)
+        try:
+            emb = r["embeddings"]
+            with self.lock:
+                if r["faiss_index"] is not None:
+                    index = faiss.deserialize_index(r["faiss_index"], device=self.device)
+                elif emb is not None:
+                    index = faiss.IndexFlatIP(emb.shape[1], device=self.device)
+                    index.reserve(emb.shape[0])
+                    expect = 0
+                    for first, rows in emb.iter_row_blocks():
+                        if first != expect:
+                            raise rvdb_reader.RvdbFormatError(f"{index_file}: embedding chunks out of order")
+                        for s in range(0, len(rows), _BUILD_CHUNK):
+                            chunk = np.array(rows[s:s + _BUILD_CHUNK], dtype=np.float32, order="C", copy=True)
+                            faiss.normalize_L2(chunk)
+                            index.add(chunk)
+                        expect += len(rows)
+                else:
+                    raise KeyError("FAISS index not found in file")
+                self.faiss_index = index
+                self.vectors = emb.read() if (load_vectors and emb is not None) else None
+                self.metadata_list = r["metadata"]
+                self.metadata_cache = {}
+                self.memory_maps = {"thumbnails": {}, "temporal": {}}
+                self.is_loaded = True
+        finally:
+            r["file"].close()
+        return {"load_time": time.time() - t0, "index_info": {"processed_files": len(self.metadata_list),
+                                                               "vector_dim": self.faiss_index.d}}
 
     # ----------------------------------------------------------------- search
     def search_vectors(self, query_vector: np.ndarray, k: int = 50,

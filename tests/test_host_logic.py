@@ -1,6 +1,9 @@
 """CPU: the Python host wrappers (result semantics, metadata join, error behaviour) with the
 oracle injected as the index backend, checked against the golden outputs of the REFERENCE'S
 OWN wrappers.  (Injection is test-only; the product constructs the CUDA index.)"""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -332,3 +335,88 @@ def test_retriever_host_logic_reproduces_the_reference_outputs(search_golden):
     assert ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], None) == 0.0
     assert abs(ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], 3 * raw[1]) - 1.0) < 1e-6
     assert ivr_b200.FAISSRetriever._calculate_proper_similarity(raw[1], -raw[1]) == 0.0            # clamped
+
+
+# ---------------------------------------------------------------------------
+# .rvdb container pieces (host only: the decoders are plain C inside the .so)
+# ---------------------------------------------------------------------------
+def test_lz4_frame_decoder_against_a_real_lz4_library():
+    """rvdb_reader.lz4_frame_decompress vs frames written by pyarrow's LZ4 codec (the real liblz4 frame writer):
+    empty, tiny, multi-block, compressible and incompressible payloads, concatenated frames."""
+    pa = pytest.importorskip("pyarrow")
+    from ivr_b200 import rvdb_reader as rr
+    rng = np.random.default_rng(0)
+    payloads = [b"", b"x", bytes(range(256)) * 3, rng.integers(0, 4, 70_000, dtype=np.uint8).tobytes(),
+                rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes(),           # incompressible: stored blocks
+                rng.integers(0, 8, 5_000_000, dtype=np.uint8).tobytes()]           # > one 4 MB block
+    for p in payloads:
+        frame = pa.compress(p, codec="lz4", asbytes=True)
+        assert frame[:4] == b"\x04\x22\x4d\x18"
+        assert rr.lz4_frame_decompress(frame) == p
+        assert rr.lz4_frame_decompress(np.frombuffer(frame, np.uint8)) == p
+    two = pa.compress(payloads[2], codec="lz4", asbytes=True) + pa.compress(payloads[3], codec="lz4", asbytes=True)
+    assert rr.lz4_frame_decompress(two) == payloads[2] + payloads[3]
+    with pytest.raises(rr.RvdbFormatError):
+        rr.lz4_frame_decompress(b"\x00\x01\x02\x03\x04\x05\x06\x07")
+    bad = bytearray(pa.compress(payloads[3], codec="lz4", asbytes=True))
+    bad[40] ^= 0xFF
+    try:                                                          # a corrupted block must fail or differ, never crash
+        assert rr.lz4_frame_decompress(bytes(bad)) != payloads[3]
+    except rr.RvdbFormatError:
+        pass
+
+
+def _rvdb_fixture(path, emb, meta, with_faiss_bytes=None, old_layout=False):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import hdf5_fixture as hf
+    import pyarrow as pa
+    w = hf.Writer()
+    frame = pa.compress(json.dumps(meta).encode(), codec="lz4", asbytes=True)
+    links = {"vectors": w.group({"embeddings": w.dataset(emb, chunks=(256, emb.shape[1]), lzf=True, do_shuffle=True,
+                                                         skip_lzf_on=(1,))}),
+             "metadata": w.group({"data": w.dataset(np.frombuffer(frame, np.uint8))}),
+             "system": w.group({"build_info": w.dataset(np.frombuffer(b'{"v": 1}', np.uint8), compact=True)})}
+    if with_faiss_bytes is not None and not old_layout:
+        links["faiss_index"] = w.dataset(np.frombuffer(with_faiss_bytes, np.uint8), chunks=(1 << 16,), lzf=True)
+    if with_faiss_bytes is not None and old_layout:
+        links["index"] = w.group({"faiss": w.dataset(np.frombuffer(
+            pa.compress(with_faiss_bytes, codec="lz4", asbytes=True), np.uint8))})
+    with open(path, "wb") as f:
+        f.write(w.finish(w.group(links)))
+
+
+def test_rvdb_reader_on_a_spec_built_container(tmp_path):
+    """HDF5 subset reader (superblock 0, v1 object headers + continuation, symbol-table groups, compact / contiguous /
+    chunked layouts with a two-level chunk B-tree, shuffle + LZF with a skipped-filter chunk) on a file assembled by
+    tests/hdf5_fixture.py from the published format -- self-consistency, NOT a file written by h5py (absent here)."""
+    pytest.importorskip("pyarrow")
+    from ivr_b200 import rvdb_reader as rr
+    rng = np.random.default_rng(1)
+    emb = rng.standard_normal((1500, 96)).astype(np.float32)
+    emb[100:400] = np.round(emb[100:400], 1)                     # compressible region
+    meta = [{"file_path": f"keyframes/L01_V001/{i:04d}.jpg", "folder_name": "L01_V001", "image_name": f"{i:04d}.jpg",
+             "frame_id": i, "file_hash": f"{i:016x}", "file_size": 1000 + i} for i in range(len(emb))]
+    path = str(tmp_path / "index.rvdb")
+    _rvdb_fixture(path, emb, meta)
+    with rr.Hdf5File(path) as f:
+        assert f.keys("/") == ["metadata", "system", "vectors"] and f.keys("vectors") == ["embeddings"]
+        assert f.is_group("vectors") and not f.is_group("vectors/embeddings") and "nope/x" not in f
+        ds = f.dataset("vectors/embeddings")
+        assert ds.shape == emb.shape and ds.dtype == np.float32 and ds.layout["chunk"] == (256, 96)
+        assert [fid for fid, _ in ds.filters] == [2, 32000]
+        assert np.array_equal(ds.read(), emb)
+        firsts, blocks = zip(*ds.iter_row_blocks())
+        assert list(firsts) == list(range(0, 1500, 256)) and np.array_equal(np.concatenate(blocks), emb)
+        assert bytes(f.dataset("system/build_info").read()) == b'{"v": 1}'
+        del ds, blocks
+    r = rr.read_rvdb(path)
+    try:
+        assert r["metadata"] == meta and r["faiss_index"] is None and r["embeddings"].shape == emb.shape
+    finally:
+        r["file"].close()
+    with open(path, "r+b") as fh:                                 # libver='latest' files are refused, not mis-read
+        fh.seek(8)
+        fh.write(b"\x02")
+    with pytest.raises(rr.RvdbFormatError, match="superblock version 2"):
+        rr.Hdf5File(path)

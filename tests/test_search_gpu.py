@@ -735,3 +735,45 @@ def test_faiss_layout_serialisation_round_trip_through_the_device(tmp_path):
         fc.deserialize_index(np.frombuffer(buf[:-8], np.uint8))
     with pytest.raises(ivr_b200._native.NativeError):
         idx.reconstruct_n(n - 1, 5)
+
+
+@pytest.mark.parametrize("layout", ["faiss_index dataset", "index/faiss (old, LZ4-framed)", "embeddings only"])
+def test_load_unified_index_from_an_rvdb_container(tmp_path, layout):
+    """UnifiedIndex.load_unified_index on a .rvdb-shaped file (tests/hdf5_fixture.py builds it from the published HDF5 /
+    LZF / LZ4 formats; metadata framed by pyarrow's real LZ4 codec): the index arrives through deserialize_index
+    (unified_index.py:1182 / 1185-1188) or is built from the embedding chunks (1755-1793), and searches like an index
+    built from the same arrays in memory."""
+    pytest.importorskip("pyarrow")
+    import os
+    import struct
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_logic import _rvdb_fixture
+    import ivr_b200
+    n, d = 3000, 96
+    emb = (synth.clip_like(n, d, seed=99, n_centres=32) * np.float32(1.7)).astype(np.float32)     # raw, un-normalised
+    meta = [{"file_path": f"keyframes/L01_V001/{i:04d}.jpg", "folder_name": "L01_V001", "image_name": f"{i:04d}.jpg",
+             "frame_id": i, "file_hash": f"{i:016x}", "file_size": 1000 + i} for i in range(n)]
+    unit = emb.copy()
+    flat_ip.normalize_L2(unit)
+    faiss_bytes = (b"IxFI" + struct.pack("<iqqq?i", d, n, 1 << 20, 1 << 20, True, 0) + struct.pack("<Q", n * d) + unit.tobytes())
+    path = str(tmp_path / "unified.rvdb")
+    _rvdb_fixture(path, emb, meta, with_faiss_bytes=None if layout == "embeddings only" else faiss_bytes,
+                  old_layout=layout.startswith("index/faiss"))
+    u = ivr_b200.UnifiedIndex()
+    info = u.load_unified_index(path)
+    assert u.is_loaded and u.faiss_index.ntotal == n and info["index_info"]["processed_files"] == n
+    assert u.metadata_list == meta and u.vectors is None
+    mem = ivr_b200.UnifiedIndex()
+    mem.build_from_embeddings(emb, meta)
+    xq = synth.clip_like(4, d, seed=100, n_centres=32)
+    for q in xq:
+        a, b = u.search_vectors(q, k=20), mem.search_vectors(q, k=20)
+        assert [h["index"] for h in a] == [h["index"] for h in b]
+        np.testing.assert_allclose([h["similarity_score"] for h in a], [h["similarity_score"] for h in b], atol=1e-6)
+        assert all(h["metadata"] is u.metadata_list[h["index"]] for h in a)
+    v = ivr_b200.load_optimized_index(path)
+    assert v.faiss_index.ntotal == n
+    w = ivr_b200.UnifiedIndex()
+    w.load_unified_index(path, load_vectors=True)
+    assert np.array_equal(w.vectors, emb)

@@ -33,6 +33,8 @@ if len(rows) > 2:
     hdr, data = rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
     stall = [h for h in hdr if h.startswith("stall_") and "(Not Issued)" not in h]
+    # several kernels in one report repeat the header block: keep the well-formed data rows only
+    data = [r for r in data if len(r) == len(hdr) and (r[ix["# Samples"]] or "0").isdigit()]
     tot = sum(int(r[ix["# Samples"]] or 0) for r in data) or 1
     print("## Warp-stall samples by reason\n\n| reason | samples | share |\n|---|---|---|")
     agg = {h: sum(int(r[ix[h]] or 0) for r in data) for h in stall}
