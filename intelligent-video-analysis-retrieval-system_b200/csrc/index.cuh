@@ -71,6 +71,12 @@ struct MergeIn {
     int     raw;             // entries are raw {score bits, row} pairs (converted to keys on load)
     int     interleave;      // lists of 32 consecutive queries are interleaved: entry i of query q lives at
                              // l*list_stride + (q / 32) * q_stride * 32 + i * 32 + q % 32
+    // DENSE mode (dense != nullptr; `entries` unused): list l of query q is the `dense_len` consecutive SCORES
+    // dense[q * dense_q_stride + l * dense_len + i], i.e. rows l * dense_len + i (< dense_rows) of a materialised
+    // score matrix; keys are formed on load.
+    const float* dense;
+    int64_t      dense_q_stride, dense_rows;
+    int          dense_len;
 };
 // final stage: writes D/I ([nq,k], padded with -FLT_MAX / -1); ids = row + id_offset;
 // scores are multiplied by q_scale[q] when q_scale != nullptr (power-of-two query scaling)

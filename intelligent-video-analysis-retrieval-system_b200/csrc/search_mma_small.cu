@@ -55,6 +55,14 @@ struct SmallParams {
     uint64_t* lists;         // [grid][4 warps][npad][C] raw candidate lists
     int*      counts;        // [grid][4 warps][npad]
     uint32_t* tau_g;         // [npad] shared per-query thresholds (order-preserving encoding)
+    // DUMP mode (small shards: dump != nullptr): no candidate lists -- every score goes to dump[q * dump_stride + row]
+    // (4 bytes per (query, row): a few % of the row bytes for the batches this kernel serves) and every 128-row tile
+    // publishes its maximum per query, tile_max[q * n_tiles + tile]; merge_select_kernel then needs only the ~k tiles
+    // whose maximum reaches the k-th largest tile maximum.  One launch, no threshold learning, no seeding launches.
+    float*    dump;
+    int64_t   dump_stride;   // floats per query (>= padded row count)
+    uint32_t* tile_max;      // zero-initialised by the caller
+    int64_t   n_tiles;       // tiles of the whole shard
 };
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32]) {
@@ -172,6 +180,40 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         };
 
         int buf = 0; uint32_t bphase = 0; int64_t n = 0;
+        if (p.dump) {
+            // ---------------- dump mode: scores + per-tile maxima, no lists ----------------
+            for (int64_t j = j0; j < j1; ++j) {
+                const int64_t tile = p.tile0 + j;
+                const int64_t row = tile * kSmallTileRows + quarter * 32 + lane;
+                const bool valid = row < p.n_rows;
+                mbar_wait(tfull_bar(buf), bphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                       static_cast<uint32_t>(buf * p.buf_cols);
+                for (int c0 = 0; c0 < p.npad; c0 += 32) {
+                    uint32_t v[32];
+                    const int ncol = min(32, p.npad - c0);
+                    if (ncol == 32) tmem_ld_32x32(taddr + c0, v);
+                    else tmem_ld_32x16(taddr + c0, v);                  // npad is a multiple of 16
+                    tmem_wait_ld(v);
+                    if (c0 + 32 >= p.npad) {                            // accumulator fully read: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_local(tempty_bar(buf));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i >= ncol) break;                           // warp-uniform
+                        const uint32_t bits = valid ? v[i] : 0xff800000u;   // rows past the end: -inf
+                        float* dst = p.dump + static_cast<int64_t>(c0 + i) * p.dump_stride + row;
+                        *dst = __uint_as_float(bits);                    // 32 consecutive rows: one 128-byte store per query
+                        const uint32_t mx = __reduce_max_sync(0xffffffffu, f2ord(__uint_as_float(bits)));
+                        if (lane == 0) atomicMax(p.tile_max + static_cast<int64_t>(c0 + i) * p.n_tiles + tile, mx);
+                    }
+                }
+                if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
+            }
+        } else
         for (int64_t j = j0; j < j1; ++j, ++n) {
             // make room: one tile adds at most 32 entries (one per lane) to each of this warp's lists
             for (int qb = 0; qb < p.npad; qb += 32) {
@@ -238,7 +280,8 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
         }
         __syncwarp();
-        for (int q = lane; q < p.npad; q += 32) p.counts[wslot * p.npad + q] = cnt_w[q];
+        if (!p.dump)
+            for (int q = lane; q < p.npad; q += 32) p.counts[wslot * p.npad + q] = cnt_w[q];
     }
 
     // ------------------------------------------------------------------ teardown ----
@@ -271,6 +314,71 @@ bool mma_small_supported(const ivr_index* idx, int64_t nq, int k) {
     return small_shape(idx, nq, k, &s);
 }
 
+// One launch in dump mode + the one-launch select (merge_select_kernel, dense input).
+static int search_mma_small_dump(ivr_index* idx, const SmallShape& sh, const float* q_dev, int64_t nq, int k, float* D_dev,
+                                 int64_t* I_dev, int64_t id_offset, cudaStream_t st) {
+    const int64_t nt = (idx->ntotal + kSmallTileRows - 1) / kSmallTileRows;
+    const int64_t stride = nt * kSmallTileRows;                      // padded rows per query
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_q  = carve(static_cast<size_t>(sh.npad) * idx->dpad * 2);
+    const size_t o_sc = carve(static_cast<size_t>(sh.npad) * 4);
+    const size_t o_tg = carve(static_cast<size_t>(sh.npad) * 4);
+    const size_t o_s  = carve(static_cast<size_t>(sh.npad) * stride * 4);
+    const size_t zero_bytes = (static_cast<size_t>(sh.npad) * nt + 2 * nq) * 4;    // tile maxima, pool counters, tickets
+    const size_t o_z  = carve(zero_bytes);
+    const size_t o_p  = carve(static_cast<size_t>(nq) * kSelectPoolCap * 8);
+    IVR_TRY(ensure_ws(idx, off));
+    char* ws = static_cast<char*>(idx->ws);
+    __half* q_h = reinterpret_cast<__half*>(ws + o_q);
+    float* q_scale = reinterpret_cast<float*>(ws + o_sc);
+    uint32_t* tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
+    uint32_t* tile_max = reinterpret_cast<uint32_t*>(ws + o_z);
+    int* pool_cnt = reinterpret_cast<int*>(tile_max + static_cast<size_t>(sh.npad) * nt);
+    const bool timed = idx->timing;
+
+    if (timed) cudaEventRecord(idx->ev[4], st);
+    IVR_TRY(launch_queries_to_f16(q_dev, q_h, q_scale, tau_g, nq, sh.npad, idx->dim, idx->dpad, st));
+    IVR_CUDA(cudaMemsetAsync(ws + o_z, 0, zero_bytes, st));
+    idx->launches[2]++;
+    if (timed) cudaEventRecord(idx->ev[5], st);
+
+    CUtensorMap tmq;
+    IVR_TRY(make_tmap(&tmq, q_h, sh.npad, idx->dpad, sh.npad));
+    if (idx->tmap_rows_base != idx->rows || idx->tmap_rows_n != idx->ntotal || idx->tmap_rows_box != kSmallTileRows) {
+        IVR_TRY(make_tmap(reinterpret_cast<CUtensorMap*>(idx->tmap_rows), idx->rows, idx->ntotal, idx->dpad, kSmallTileRows));
+        idx->tmap_rows_base = idx->rows; idx->tmap_rows_n = idx->ntotal; idx->tmap_rows_box = kSmallTileRows;
+    }
+    const CUtensorMap& tmx = *reinterpret_cast<const CUtensorMap*>(idx->tmap_rows);
+    IVR_CUDA(cudaFuncSetAttribute(search_mma_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(sh.smem)));
+    SmallParams p{};
+    p.n_rows = idx->ntotal; p.nq = static_cast<int>(nq); p.npad = sh.npad; p.k = k; p.C = sh.C;
+    p.kblocks = idx->dpad / kKBlock; p.stages = sh.stages; p.nbuf = sh.nbuf; p.buf_cols = sh.buf_cols;
+    p.tile0 = 0; p.nt = nt;
+    p.row_policy = kL2EvictFirst;
+    p.tau_g = tau_g;
+    p.dump = reinterpret_cast<float*>(ws + o_s); p.dump_stride = stride; p.tile_max = tile_max; p.n_tiles = nt;
+    const int grid = static_cast<int>(std::min<int64_t>(idx->sm_count, std::max<int64_t>(nt, 1)));
+    if (timed) cudaEventRecord(idx->ev[0], st);
+    search_mma_small_kernel<<<grid, kSmallThreads, sh.smem, st>>>(tmq, tmx, p);
+    IVR_CUDA(cudaGetLastError());
+    idx->launches[0]++;
+    if (timed) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
+    MergeIn in{};
+    in.dense = p.dump; in.dense_q_stride = stride; in.dense_rows = idx->ntotal; in.dense_len = kSmallTileRows;
+    in.cnt_list_stride = 1; in.cnt_q_stride = nt;                   // strides of the maxima array
+    in.n_lists = static_cast<int>(nt);
+    IVR_TRY(merge_select_final(in, tile_max, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_p),
+                               pool_cnt, pool_cnt + nq, idx->sm_count, st, &idx->launches[1], q_scale));
+    if (timed) {
+        cudaEventRecord(idx->ev[3], st);
+        idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
+    }
+    idx->last_kernel = "search_mma_small_kernel";
+    return IVR_OK;
+}
+
 int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                      int64_t id_offset, cudaStream_t st) {
     SmallShape sh;
@@ -278,6 +386,12 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
                                                    static_cast<long long>(nq), k, idx->dim); return IVR_EUNSUPPORTED; }
     const int64_t nt = (idx->ntotal + kSmallTileRows - 1) / kSmallTileRows;
     const int sms = idx->sm_count;
+    // Small shards: one launch that materialises the scores (see SmallParams::dump).  The seeded candidate-list path
+    // pays ~0.2 ms of fixed cost (2-3 launches, their merges, cold lists): 1 M x 512 x 16 queries ran at 0.36 ms against
+    // an HBM floor of 0.16.  Writing the scores costs nq * 4 bytes per row; it wins while that stays below those 0.2 ms.
+    const int64_t dump_elems = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_MELEMS", 128)) << 20;
+    if (k <= kSelectMaxK && nt * kSmallTileRows * sh.npad <= dump_elems && nt <= 65536)
+        return search_mma_small_dump(idx, sh, q_dev, nq, k, D_dev, I_dev, id_offset, st);
     // launch boundaries (in row tiles): one tile per CTA, then as many rows as keep the expected admissions per
     // list around 64 (k * rows_now / rows_before spread over 4 * sms lists), then the rest
     int64_t bounds[4] = {0, 0, 0, 0};

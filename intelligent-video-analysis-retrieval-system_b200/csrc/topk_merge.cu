@@ -32,6 +32,15 @@ struct MergeOut {
 template <typename F>
 __device__ __forceinline__ void for_each_key(const MergeIn& in, int64_t q, int l0, int l1, F&& f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (in.dense) {                                  // materialised scores: rows l * dense_len + i
+        const float* base = in.dense + q * in.dense_q_stride;
+        for (int l = l0 + warp; l < l1; l += nwarps)
+            for (int i = lane; i < in.dense_len; i += 32) {
+                const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                if (row < in.dense_rows) f(make_key(base[row], static_cast<uint32_t>(row)));
+            }
+        return;
+    }
     for (int l = l0 + warp; l < l1; l += nwarps) {
         const int cnt = in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride]
                                   : in.fixed_count;
@@ -256,14 +265,22 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
     const int l0 = blockIdx.x * per, l1 = min(l0 + per, M);
     for (int l = l0 + warp; l < l1; l += nwarps) {
         if (sa.maxima[l * in.cnt_list_stride + q * in.cnt_q_stride] < T) continue;     // nothing of this list can survive
-        const int cnt = in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count;
-        const uint64_t* base = in.entries + l * in.list_stride +
+        const int cnt = in.dense ? in.dense_len
+                                 : (in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count);
+        const uint64_t* base = in.dense ? nullptr : in.entries + l * in.list_stride +
                                (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
         const int es = in.interleave ? 32 : 1;
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             const int i = i0 + lane;
-            uint64_t key = (i < cnt) ? base[static_cast<int64_t>(i) * es] : 0ull;
-            if (in.raw && i < cnt) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+            uint64_t key = 0ull;
+            if (in.dense) {
+                const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                if (i < cnt && row < in.dense_rows)
+                    key = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
+            } else if (i < cnt) {
+                key = base[static_cast<int64_t>(i) * es];
+            }
+            if (!in.dense && in.raw && i < cnt) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
             const bool keep = key != 0ull && static_cast<uint32_t>(key >> 32) >= T;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (m) {
@@ -358,7 +375,7 @@ int merge_select_final(const MergeIn& in, const uint32_t* maxima, int64_t nq, in
     out.D = D_dev; out.I = I_dev; out.id_offset = id_offset; out.nq = nq; out.q_scale = q_scale;
     SelectArgs sa{maxima, pool, pool_cnt, ticket, kSelectPoolCap};
     // enough CTAs that the filter pass is spread over the machine, few enough that the redundant T search stays cheap
-    const int ctas = std::max(1, std::min(in.n_lists / 16, std::max(1, sm_count / static_cast<int>(std::min<int64_t>(nq, 4)))));
+    const int ctas = std::max(1, std::min(in.n_lists / 16, std::max(1, 2 * sm_count / static_cast<int>(std::min<int64_t>(nq, 2 * sm_count)))));
     dim3 grid(static_cast<unsigned>(ctas), static_cast<unsigned>(nq));
     merge_select_kernel<<<grid, kMergeThreads, smem, st>>>(in, out, sa, k, kpad);
     IVR_CUDA(cudaGetLastError());

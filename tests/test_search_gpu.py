@@ -133,10 +133,14 @@ def test_mma_two_phase_large_shard(mode, monkeypatch):
     assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
 
 
-@pytest.fixture
-def small_kernel(monkeypatch):
-    """Force the small-batch (operand-swapped, row-streaming) tcgen05 kernel."""
+@pytest.fixture(params=["lists", "dump"])
+def small_kernel(request, monkeypatch):
+    """Force the small-batch (operand-swapped, row-streaming) tcgen05 kernel, in both of its result modes:
+    seeded candidate lists (large shards) and materialised scores + tile maxima (small shards)."""
     monkeypatch.setenv("IVR_MMA_MODE", "3")
+    if request.param == "lists":
+        monkeypatch.setenv("IVR_SMALL_DUMP_MAX_MELEMS", "0")
+    return request.param
 
 
 @pytest.mark.parametrize("d", [512, 768, 1024, 384, 100, 64])
@@ -192,6 +196,8 @@ def test_small_kernel_unsupported_shapes_fall_back_in_auto_mode_and_fail_loudly_
 @pytest.mark.parametrize("ratio", [0, 2], ids=["two_launches", "three_launches"])
 def test_small_kernel_seeded_launches_match_single_launch(ratio, small_kernel, monkeypatch):
     """Shards of >= 4 tiles per SM are searched in 2-3 launches, each seeding the next one's thresholds."""
+    if small_kernel == "dump":
+        pytest.skip("seeding launches belong to the candidate-list mode")
     if ratio:
         monkeypatch.setenv("IVR_MMA_SMALL_RATIO", str(ratio))
     xb = synth.clip_like(300_000, 64, seed=91, n_centres=512)
@@ -777,3 +783,20 @@ def test_load_unified_index_from_an_rvdb_container(tmp_path, layout):
     w = ivr_b200.UnifiedIndex()
     w.load_unified_index(path, load_vectors=True)
     assert np.array_equal(w.vectors, emb)
+
+
+def test_small_kernel_dump_mode_clustered_rows_overflow_the_pool_and_stay_exact(monkeypatch):
+    """Dump mode bounds the k-th best by the k-th largest TILE maximum.  5000 near-identical rows packed into ~40
+    consecutive tiles make that bound useless (every one of them passes it): the candidate pool overflows and the
+    kernel falls back to the exact radix select -- slow, but the result must still be exact."""
+    monkeypatch.setenv("IVR_MMA_MODE", "3")
+    rng = np.random.default_rng(7)
+    d, n = 64, 40_000
+    xb = synth.gaussian_unit(n, d, seed=70)
+    q = synth.gaussian_unit(3, d, seed=71)
+    hot = q[0] + 0.02 * rng.standard_normal((5000, d)).astype(np.float32)      # a burst of near-duplicates of query 0
+    xb[10_000:15_000] = hot / np.linalg.norm(hot, axis=1, keepdims=True)
+    idx, ref = build(np.ascontiguousarray(xb, dtype=np.float32))
+    check(idx, ref, q, 100, path=2)
+    check(idx, ref, q, 1000, path=2)
+    assert idx.last_timing()["kernel"] == "search_mma_small_kernel"
