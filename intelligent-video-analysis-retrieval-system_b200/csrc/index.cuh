@@ -88,7 +88,8 @@ constexpr int kSelectMaxK    = 1024;
 constexpr int kSelectPoolCap = 4096;
 int merge_select_final(const MergeIn& in, const uint32_t* maxima, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                        int64_t id_offset, uint64_t* pool, int* pool_cnt, int* ticket, int sm_count, cudaStream_t st,
-                       int* n_launches, const float* q_scale = nullptr);
+                       int* n_launches, const float* q_scale = nullptr,
+                       const uint32_t* group_max = nullptr, int n_groups = 0);   // [nq][n_groups]: bound searched in these
 int merge_lists_keys(const MergeIn& in, int64_t nq, int k, uint64_t* out_keys, int* out_counts,
                      uint64_t* tmp_entries, int* tmp_counts, cudaStream_t st, int* n_launches);
 size_t merge_tmp_entries(int n_lists, int64_t nq, int k);   // #keys of scratch the merge may need

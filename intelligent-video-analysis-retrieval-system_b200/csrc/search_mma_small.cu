@@ -63,6 +63,8 @@ struct SmallParams {
     int64_t   dump_stride;   // floats per query (>= padded row count)
     uint32_t* tile_max;      // zero-initialised by the caller
     int64_t   n_tiles;       // tiles of the whole shard
+    uint32_t* group_max;     // [npad][n_groups]: maxima of n_groups runs of consecutive tiles (zero-initialised)
+    int       n_groups;
 };
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32]) {
@@ -184,6 +186,7 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             // ---------------- dump mode: scores + per-tile maxima, no lists ----------------
             for (int64_t j = j0; j < j1; ++j) {
                 const int64_t tile = p.tile0 + j;
+                const int64_t grp = tile * p.n_groups / p.n_tiles;
                 const int64_t row = tile * kSmallTileRows + quarter * 32 + lane;
                 const bool valid = row < p.n_rows;
                 mbar_wait(tfull_bar(buf), bphase);
@@ -208,7 +211,10 @@ search_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         float* dst = p.dump + static_cast<int64_t>(c0 + i) * p.dump_stride + row;
                         *dst = __uint_as_float(bits);                    // 32 consecutive rows: one 128-byte store per query
                         const uint32_t mx = __reduce_max_sync(0xffffffffu, f2ord(__uint_as_float(bits)));
-                        if (lane == 0) atomicMax(p.tile_max + static_cast<int64_t>(c0 + i) * p.n_tiles + tile, mx);
+                        if (lane == 0) {
+                            atomicMax(p.tile_max + static_cast<int64_t>(c0 + i) * p.n_tiles + tile, mx);
+                            atomicMax(p.group_max + static_cast<int64_t>(c0 + i) * p.n_groups + grp, mx);
+                        }
                     }
                 }
                 if (++buf == p.nbuf) { buf = 0; bphase ^= 1; }
@@ -325,7 +331,8 @@ static int search_mma_small_dump(ivr_index* idx, const SmallShape& sh, const flo
     const size_t o_sc = carve(static_cast<size_t>(sh.npad) * 4);
     const size_t o_tg = carve(static_cast<size_t>(sh.npad) * 4);
     const size_t o_s  = carve(static_cast<size_t>(sh.npad) * stride * 4);
-    const size_t zero_bytes = (static_cast<size_t>(sh.npad) * nt + 2 * nq) * 4;    // tile maxima, pool counters, tickets
+    const int n_groups = static_cast<int>(std::min<int64_t>(nt, 1024));
+    const size_t zero_bytes = (static_cast<size_t>(sh.npad) * (nt + n_groups) + 2 * nq) * 4;   // tile + group maxima, pool counters, tickets
     const size_t o_z  = carve(zero_bytes);
     const size_t o_p  = carve(static_cast<size_t>(nq) * kSelectPoolCap * 8);
     IVR_TRY(ensure_ws(idx, off));
@@ -334,7 +341,8 @@ static int search_mma_small_dump(ivr_index* idx, const SmallShape& sh, const flo
     float* q_scale = reinterpret_cast<float*>(ws + o_sc);
     uint32_t* tau_g = reinterpret_cast<uint32_t*>(ws + o_tg);
     uint32_t* tile_max = reinterpret_cast<uint32_t*>(ws + o_z);
-    int* pool_cnt = reinterpret_cast<int*>(tile_max + static_cast<size_t>(sh.npad) * nt);
+    uint32_t* group_max = tile_max + static_cast<size_t>(sh.npad) * nt;
+    int* pool_cnt = reinterpret_cast<int*>(group_max + static_cast<size_t>(sh.npad) * n_groups);
     const bool timed = idx->timing;
 
     if (timed) cudaEventRecord(idx->ev[4], st);
@@ -359,6 +367,7 @@ static int search_mma_small_dump(ivr_index* idx, const SmallShape& sh, const flo
     p.row_policy = kL2EvictFirst;
     p.tau_g = tau_g;
     p.dump = reinterpret_cast<float*>(ws + o_s); p.dump_stride = stride; p.tile_max = tile_max; p.n_tiles = nt;
+    p.group_max = group_max; p.n_groups = n_groups;
     const int grid = static_cast<int>(std::min<int64_t>(idx->sm_count, std::max<int64_t>(nt, 1)));
     if (timed) cudaEventRecord(idx->ev[0], st);
     search_mma_small_kernel<<<grid, kSmallThreads, sh.smem, st>>>(tmq, tmx, p);
@@ -370,7 +379,7 @@ static int search_mma_small_dump(ivr_index* idx, const SmallShape& sh, const flo
     in.cnt_list_stride = 1; in.cnt_q_stride = nt;                   // strides of the maxima array
     in.n_lists = static_cast<int>(nt);
     IVR_TRY(merge_select_final(in, tile_max, nq, k, D_dev, I_dev, id_offset, reinterpret_cast<uint64_t*>(ws + o_p),
-                               pool_cnt, pool_cnt + nq, idx->sm_count, st, &idx->launches[1], q_scale));
+                               pool_cnt, pool_cnt + nq, idx->sm_count, st, &idx->launches[1], q_scale, group_max, n_groups));
     if (timed) {
         cudaEventRecord(idx->ev[3], st);
         idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;
@@ -390,7 +399,8 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
     // pays ~0.2 ms of fixed cost (2-3 launches, their merges, cold lists): 1 M x 512 x 16 queries ran at 0.36 ms against
     // an HBM floor of 0.16.  Writing the scores costs nq * 4 bytes per row; it wins while that stays below those 0.2 ms.
     const int64_t dump_elems = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_MELEMS", 128)) << 20;
-    if (k <= kSelectMaxK && nt * kSmallTileRows * sh.npad <= dump_elems && nt <= 65536)
+    const int64_t dump_rows = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_KROWS", 4000)) * 1000;
+    if (k <= kSelectMaxK && nt * kSmallTileRows * sh.npad <= dump_elems && nt * kSmallTileRows <= dump_rows)
         return search_mma_small_dump(idx, sh, q_dev, nq, k, D_dev, I_dev, id_offset, st);
     // launch boundaries (in row tiles): one tile per CTA, then as many rows as keep the expected admissions per
     // list around 64 (k * rows_now / rows_before spread over 4 * sms lists), then the rest

@@ -197,6 +197,12 @@ merge_kernel(MergeIn in, MergeOut out, int lists_per_group, int k, int kpad) {
 // ---------------------------------------------------------------------------
 struct SelectArgs {
     const uint32_t* maxima;     // [n_lists * cnt_list_stride ...] ordered-score maximum of every list (same strides as counts)
+    // the values the bound T is searched in: maximum g of query q at tmax[g * t_stride_g + q * t_stride_q], g < n_t.
+    // Either the list maxima themselves, or the maxima of <= 1024 GROUPS of consecutive lists (dense mode: ~10^4 .. 10^5
+    // tiles per query would make the redundant per-CTA search the dominant cost; ~1000 groups bound just as tightly).
+    const uint32_t* tmax;
+    int64_t   t_stride_g, t_stride_q;
+    int       n_t;
     uint64_t* pool;             // [nq][pool_cap]
     int*      pool_cnt;         // [nq]
     int*      ticket;           // [nq]
@@ -213,7 +219,7 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int M = in.n_lists;
 
-    // ---- 1. T = k-th largest list maximum (0 when fewer than k lists have entries: admit everything) ----
+    // ---- 1. T = k-th largest (group) maximum (0 when fewer than k of them are set: admit everything) ----
     {
         uint32_t prefix = 0, mask = 0;
         int remaining = k;
@@ -221,8 +227,8 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
             const int shift = 24 - 8 * pass;
             for (int i = tid; i < 256; i += blockDim.x) sh.hist[i] = 0;
             __syncthreads();
-            for (int l = tid; l < M; l += blockDim.x) {
-                const uint32_t v = sa.maxima[l * in.cnt_list_stride + q * in.cnt_q_stride];
+            for (int g = tid; g < sa.n_t; g += blockDim.x) {
+                const uint32_t v = sa.tmax[g * sa.t_stride_g + q * sa.t_stride_q];
                 if ((v & mask) == prefix) atomicAdd(&sh.hist[(v >> shift) & 0xff], 1);
             }
             __syncthreads();
@@ -263,31 +269,37 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
     uint64_t* pool = sa.pool + q * sa.pool_cap;
     const int per = (M + gridDim.x - 1) / gridDim.x;
     const int l0 = blockIdx.x * per, l1 = min(l0 + per, M);
-    for (int l = l0 + warp; l < l1; l += nwarps) {
-        if (sa.maxima[l * in.cnt_list_stride + q * in.cnt_q_stride] < T) continue;     // nothing of this list can survive
-        const int cnt = in.dense ? in.dense_len
-                                 : (in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count);
-        const uint64_t* base = in.dense ? nullptr : in.entries + l * in.list_stride +
-                               (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
-        const int es = in.interleave ? 32 : 1;
-        for (int i0 = 0; i0 < cnt; i0 += 32) {
-            const int i = i0 + lane;
-            uint64_t key = 0ull;
-            if (in.dense) {
-                const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
-                if (i < cnt && row < in.dense_rows)
-                    key = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
-            } else if (i < cnt) {
-                key = base[static_cast<int64_t>(i) * es];
-            }
-            if (!in.dense && in.raw && i < cnt) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
-            const bool keep = key != 0ull && static_cast<uint32_t>(key >> 32) >= T;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-                int pos = 0;
-                if (lane == 0) pos = atomicAdd(sa.pool_cnt + q, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                if (keep && pos < sa.pool_cap) pool[pos] = key;
+    for (int lb = l0 + warp * 32; lb < l1; lb += nwarps * 32) {      // 32 lists per step: one maximum per lane
+        const int lmine = lb + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, lmine < l1 &&
+                                      sa.maxima[lmine * in.cnt_list_stride + q * in.cnt_q_stride] >= T);
+        while (todo) {                                               // lists with a maximum below T cannot contribute
+            const int l = lb + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int cnt = in.dense ? in.dense_len
+                                     : (in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count);
+            const uint64_t* base = in.dense ? nullptr : in.entries + l * in.list_stride +
+                                   (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+            const int es = in.interleave ? 32 : 1;
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
+                const int i = i0 + lane;
+                uint64_t key = 0ull;
+                if (in.dense) {
+                    const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                    if (i < cnt && row < in.dense_rows)
+                        key = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
+                } else if (i < cnt) {
+                    key = base[static_cast<int64_t>(i) * es];
+                    if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+                }
+                const bool keep = key != 0ull && static_cast<uint32_t>(key >> 32) >= T;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(sa.pool_cnt + q, __popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < sa.pool_cap) pool[pos] = key;
+                }
             }
         }
     }
@@ -366,14 +378,17 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
 // `pool` holds nq * kSelectPoolCap keys, `pool_cnt` / `ticket` nq ints each, all zero on entry (the kernel re-zeroes them).
 int merge_select_final(const MergeIn& in, const uint32_t* maxima, int64_t nq, int k, float* D_dev, int64_t* I_dev,
                        int64_t id_offset, uint64_t* pool, int* pool_cnt, int* ticket, int sm_count, cudaStream_t st,
-                       int* n_launches, const float* q_scale) {
+                       int* n_launches, const float* q_scale, const uint32_t* group_max, int n_groups) {
     if (nq <= 0) return IVR_OK;
     if (k > kSelectMaxK || nq > 65535) { set_error("merge_select: k=%d / nq=%lld outside its range", k, static_cast<long long>(nq)); return IVR_EINVAL; }
     const int kpad = kpad_for(k);
     const size_t smem = static_cast<size_t>(std::max(kpad, kSelectPoolCap)) * sizeof(uint64_t);
     MergeOut out{};
     out.D = D_dev; out.I = I_dev; out.id_offset = id_offset; out.nq = nq; out.q_scale = q_scale;
-    SelectArgs sa{maxima, pool, pool_cnt, ticket, kSelectPoolCap};
+    SelectArgs sa{};
+    sa.maxima = maxima; sa.pool = pool; sa.pool_cnt = pool_cnt; sa.ticket = ticket; sa.pool_cap = kSelectPoolCap;
+    if (group_max) { sa.tmax = group_max; sa.t_stride_g = 1; sa.t_stride_q = n_groups; sa.n_t = n_groups; }
+    else { sa.tmax = maxima; sa.t_stride_g = in.cnt_list_stride; sa.t_stride_q = in.cnt_q_stride; sa.n_t = in.n_lists; }
     // enough CTAs that the filter pass is spread over the machine, few enough that the redundant T search stays cheap
     const int ctas = std::max(1, std::min(in.n_lists / 16, std::max(1, 2 * sm_count / static_cast<int>(std::min<int64_t>(nq, 2 * sm_count)))));
     dim3 grid(static_cast<unsigned>(ctas), static_cast<unsigned>(nq));
