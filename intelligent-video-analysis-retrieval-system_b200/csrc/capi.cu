@@ -164,6 +164,8 @@ int ivr_index_create(int dim, int device, ivr_index** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&idx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->rows_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&idx->sel_state), 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->sel_state, 0, 256);
     if (e != cudaSuccess) {
         set_error("index_create: %s", cudaGetErrorString(e));
         delete idx;
@@ -180,6 +182,7 @@ int ivr_index_destroy(ivr_index* idx) {
     if (idx->rows) cudaFree(idx->rows);
     if (idx->ws) cudaFree(idx->ws);
     if (idx->io) cudaFree(idx->io);
+    if (idx->sel_state) cudaFree(idx->sel_state);
     if (idx->pin) cudaFreeHost(idx->pin);
     for (auto& ev : idx->ev) if (ev) cudaEventDestroy(ev);
     if (idx->rows_ready) cudaEventDestroy(idx->rows_ready);

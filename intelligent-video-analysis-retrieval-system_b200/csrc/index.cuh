@@ -23,6 +23,8 @@ struct ivr_index {
     // pinned host staging
     void*   pin      = nullptr;
     size_t  pin_bytes = 0;
+    // counters / tickets of the one-launch select merge (topk_merge.cu): zeroed at creation, re-zeroed by the kernel itself
+    int*    sel_state = nullptr;
 
     // TMA descriptor cache for the MMA path (opaque 128-byte CUtensorMap blobs)
     alignas(64) unsigned char tmap_rows[128];

@@ -396,11 +396,13 @@ int search_mma_small(ivr_index* idx, const float* q_dev, int64_t nq, int k, floa
     const int64_t nt = (idx->ntotal + kSmallTileRows - 1) / kSmallTileRows;
     const int sms = idx->sm_count;
     // Small shards: one launch that materialises the scores (see SmallParams::dump).  The seeded candidate-list path
-    // pays ~0.2 ms of fixed cost (2-3 launches, their merges, cold lists): 1 M x 512 x 16 queries ran at 0.36 ms against
-    // an HBM floor of 0.16.  Writing the scores costs nq * 4 bytes per row; it wins while that stays below those 0.2 ms.
-    const int64_t dump_elems = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_MELEMS", 128)) << 20;
-    const int64_t dump_rows = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_KROWS", 4000)) * 1000;
-    if (k <= kSelectMaxK && nt * kSmallTileRows * sh.npad <= dump_elems && nt * kSmallTileRows <= dump_rows)
+    // pays ~0.2 ms of fixed cost (2-3 launches, their merges, cold lists); writing the scores costs nq * 4 bytes per
+    // row.  Measured (dump vs lists, ms): 1 M x 512: 16 q 0.26 vs 0.37, 32 q 0.30 vs 0.37, 64 q 0.44 vs 0.41;
+    // 851 k x 768: 16 q 0.30 vs 0.41, 64 q 0.37 vs 0.43; 3 M x 512: 16 q 0.64 vs 0.68, 32 q 0.72 vs 0.68; 4 M: equal;
+    // 6 M: lists win.  Rule: up to 3.5 M rows while the scores add at most 1/6 to the row bytes.
+    // IVR_SMALL_DUMP_MAX_KROWS (0 = never) overrides the row limit: tests use it to reach both modes.
+    const int64_t dump_rows = static_cast<int64_t>(env_int("IVR_SMALL_DUMP_MAX_KROWS", 3500)) * 1000;
+    if (k <= kSelectMaxK && idx->ntotal <= dump_rows && sh.npad * 4 * 6 <= idx->dpad * 2)
         return search_mma_small_dump(idx, sh, q_dev, nq, k, D_dev, I_dev, id_offset, st);
     // launch boundaries (in row tiles): one tile per CTA, then as many rows as keep the expected admissions per
     // list around 64 (k * rows_now / rows_before spread over 4 * sms lists), then the rest

@@ -30,7 +30,8 @@ constexpr int kUnroll        = 2;              // steps in flight
 template <int NQ, int DCH, int E>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
-                     const float* __restrict__ q,      // [NQ, dpad] fp32
+                     const float* __restrict__ q,      // [nq_real, dim] fp32, as the caller passed them
+                     int dim, int nq_real,
                      int k, int C, uint64_t* __restrict__ lists, int* __restrict__ counts,
                      uint32_t* __restrict__ maxima) {
     extern __shared__ float s_q[];                     // NQ * dpad
@@ -38,7 +39,11 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
     const int sub = lane & 7, rgrp = lane >> 3;
     const int nch = (DCH > 0) ? DCH : dpad / 64;       // 64-element chunks per row
 
-    for (int i = threadIdx.x; i < NQ * dpad; i += blockDim.x) s_q[i] = q[i];
+    // queries -> shared memory, zero-padded to dpad columns / NQ rows (no separate padding launch)
+    for (int i = threadIdx.x; i < NQ * dpad; i += blockDim.x) {
+        const int r = i / dpad, c = i - r * dpad;
+        s_q[i] = (r < nq_real && c < dim) ? q[static_cast<int64_t>(r) * dim + c] : 0.f;
+    }
     __syncthreads();
 
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kStreamWarps + warp;
@@ -155,7 +160,7 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
 }
 
 template <int NQ, int E>
-static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint64_t* lists, int* counts,
+static int launch_stream(ivr_index* idx, const float* q, int nq_real, int k, int C, uint64_t* lists, int* counts,
                          uint32_t* maxima, int grid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(NQ) * idx->dpad * sizeof(float);
     const int dch = idx->dpad / 64;
@@ -165,8 +170,8 @@ static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint6
         if (smem > 48 * 1024)                                                                      \
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                           static_cast<int>(smem)));                                \
-        kern<<<grid, kStreamThreads, smem, st>>>(idx->rows, idx->ntotal, idx->dpad, q_pad, k, C,   \
-                                                 lists, counts, maxima);                           \
+        kern<<<grid, kStreamThreads, smem, st>>>(idx->rows, idx->ntotal, idx->dpad, q, idx->dim,   \
+                                                 nq_real, k, C, lists, counts, maxima);            \
     } while (0)
     switch (dch) {
         case 8:  IVR_LAUNCH_STREAM(8);  break;     // 512  (CLIP ViT-B/32)
@@ -179,24 +184,13 @@ static int launch_stream(ivr_index* idx, const float* q_pad, int k, int C, uint6
 }
 
 template <int E>
-static int launch_stream_nq(ivr_index* idx, int nq, const float* q_pad, int k, int C, uint64_t* lists,
+static int launch_stream_nq(ivr_index* idx, int nq, int nq_real, const float* q, int k, int C, uint64_t* lists,
                             int* counts, uint32_t* maxima, int grid, cudaStream_t st) {
     switch (nq) {                                  // nq == 3 runs as 4 with a zero query
-        case 1: return launch_stream<1, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
-        case 2: return launch_stream<2, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
-        default: return launch_stream<4, E>(idx, q_pad, k, C, lists, counts, maxima, grid, st);
+        case 1: return launch_stream<1, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
+        case 2: return launch_stream<2, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
+        default: return launch_stream<4, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
     }
-}
-
-// fp32 [nq, dim] -> fp32 [nq, dpad] zero padded; also zeroes the merge's pool counters / tickets (2 * kStreamMaxNq ints)
-__global__ void pad_queries_kernel(const float* __restrict__ q, float* __restrict__ out,
-                                   int64_t nq_real, int64_t nq_out, int dim, int dpad, int* __restrict__ merge_state) {
-    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (i < 2 * kStreamMaxNq) merge_state[i] = 0;
-    if (i >= nq_out * dpad) return;
-    const int64_t r = i / dpad;
-    const int c = static_cast<int>(i % dpad);
-    out[i] = (c < dim && r < nq_real) ? q[r * dim + c] : 0.f;
 }
 
 int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
@@ -207,43 +201,33 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
     const int64_t n_lists = static_cast<int64_t>(grid) * kStreamWarps;
 
     // workspace carve-up
-    const size_t q_bytes = static_cast<size_t>(kStreamMaxNq) * idx->dpad * sizeof(float);
     const size_t list_keys = static_cast<size_t>(n_lists) * kStreamMaxNq * C;
     const size_t tmp_keys = merge_tmp_entries(static_cast<int>(n_lists), kStreamMaxNq, k);
     const size_t cnt_ints = static_cast<size_t>(n_lists) * kStreamMaxNq * 2 + 1024;
     const bool select = k <= kSelectMaxK;             // one-launch merge by the list-maxima bound; exact radix levels above
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_q = carve(q_bytes), o_l = carve(list_keys * 8), o_t = carve(tmp_keys * 8),
+    const size_t o_l = carve(list_keys * 8), o_t = carve(tmp_keys * 8),
                  o_c = carve(cnt_ints * 4), o_m = carve(static_cast<size_t>(n_lists) * kStreamMaxNq * 4),
-                 o_p = carve(static_cast<size_t>(kStreamMaxNq) * kSelectPoolCap * 8), o_s = carve(2 * kStreamMaxNq * 4);
+                 o_p = carve(static_cast<size_t>(kStreamMaxNq) * kSelectPoolCap * 8);
     IVR_TRY(ensure_ws(idx, off));
     char* ws = static_cast<char*>(idx->ws);
-    float* q_pad = reinterpret_cast<float*>(ws + o_q);
     uint64_t* lists = reinterpret_cast<uint64_t*>(ws + o_l);
     uint64_t* tmp = reinterpret_cast<uint64_t*>(ws + o_t);
     int* counts = reinterpret_cast<int*>(ws + o_c);
     int* tmp_counts = counts + n_lists * kStreamMaxNq;
     uint32_t* maxima = reinterpret_cast<uint32_t*>(ws + o_m);
     uint64_t* pool = reinterpret_cast<uint64_t*>(ws + o_p);
-    int* merge_state = reinterpret_cast<int*>(ws + o_s);      // [kStreamMaxNq] pool counters, [kStreamMaxNq] tickets
+    int* merge_state = idx->sel_state;                        // [kStreamMaxNq] pool counters, [kStreamMaxNq] tickets: zero between calls
 
     for (int64_t q0 = 0; q0 < nq; q0 += kStreamMaxNq) {
         const int b_real = static_cast<int>(nq - q0 < kStreamMaxNq ? nq - q0 : kStreamMaxNq);
         const int b = (b_real == 3) ? 4 : b_real;             // kernel batch (3 is padded to 4)
-        if (idx->timing && q0 == 0) cudaEventRecord(idx->ev[4], st);
-        {
-            const int64_t n = static_cast<int64_t>(b) * idx->dpad;
-            pad_queries_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-                q_dev + q0 * idx->dim, q_pad, b_real, b, idx->dim, idx->dpad, merge_state);
-            IVR_CUDA(cudaGetLastError());
-            idx->launches[2]++;
-        }
-        if (idx->timing && q0 == 0) { cudaEventRecord(idx->ev[5], st); cudaEventRecord(idx->ev[0], st); }
+        if (idx->timing && q0 == 0) { cudaEventRecord(idx->ev[4], st); cudaEventRecord(idx->ev[5], st); cudaEventRecord(idx->ev[0], st); }
         int rc;
         switch (kcap) {
-            case 128: rc = launch_stream_nq<8>(idx, b, q_pad, k, C, lists, counts, maxima, grid, st); break;   // k <= 128: register sort
-            default:  rc = launch_stream_nq<0>(idx, b, q_pad, k, C, lists, counts, maxima, grid, st); break;   // larger k: in-memory sort
+            case 128: rc = launch_stream_nq<8>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, grid, st); break;   // k <= 128: register sort
+            default:  rc = launch_stream_nq<0>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, grid, st); break;   // larger k: in-memory sort
         }
         IVR_TRY(rc);
         idx->launches[0]++;

@@ -138,8 +138,7 @@ def small_kernel(request, monkeypatch):
     """Force the small-batch (operand-swapped, row-streaming) tcgen05 kernel, in both of its result modes:
     seeded candidate lists (large shards) and materialised scores + tile maxima (small shards)."""
     monkeypatch.setenv("IVR_MMA_MODE", "3")
-    if request.param == "lists":
-        monkeypatch.setenv("IVR_SMALL_DUMP_MAX_MELEMS", "0")
+    monkeypatch.setenv("IVR_SMALL_DUMP_MAX_KROWS", "0" if request.param == "lists" else "100000")
     return request.param
 
 
@@ -791,7 +790,7 @@ def test_small_kernel_dump_mode_clustered_rows_overflow_the_pool_and_stay_exact(
     kernel falls back to the exact radix select -- slow, but the result must still be exact."""
     monkeypatch.setenv("IVR_MMA_MODE", "3")
     rng = np.random.default_rng(7)
-    d, n = 64, 40_000
+    d, n = 512, 40_000                                             # 3 queries x 512 dims: the dump-mode shape rule holds
     xb = synth.gaussian_unit(n, d, seed=70)
     q = synth.gaussian_unit(3, d, seed=71)
     hot = q[0] + 0.02 * rng.standard_normal((5000, d)).astype(np.float32)      # a burst of near-duplicates of query 0
