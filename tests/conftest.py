@@ -91,3 +91,13 @@ def relationships_golden():
     with open(os.path.join(GOLDEN, "relationships.json")) as f:
         graph = json.load(f)["graph"]
     return {"features": feats, "graph": graph}
+
+
+@pytest.fixture(scope="session")
+def chain_golden():
+    """Outputs of the reference's own inline keep-chain rules (tests/golden/make_golden_chain.py)."""
+    import json
+    arrs = dict(np.load(os.path.join(GOLDEN, "chain_rules.npz")))
+    with open(os.path.join(GOLDEN, "chain_rules.json")) as f:
+        cases = json.load(f)
+    return {"arrays": arrs, "cases": cases}

@@ -271,3 +271,16 @@ def test_frame_filter_window_above_the_mask_width_uses_the_scene_list_path():
         pytest.skip("a scene longer than the mask width: the reference semantics need window > 32 there")
     kept = ff.FrameFilter(window=40, threshold=0.95).apply_filters(x)
     assert np.array_equal(kept, np.flatnonzero(want))
+
+
+def test_inline_keep_chain_rules_on_gpu_match_the_reference(chain_golden):
+    """ivr_dedup_chain (video_frame_filter rule) and ivr_dedup_fifo (Phase 4 of filter_research_update) against the
+    kept frames the reference's own statements produced (guard-banded data: bit-identical keep lists)."""
+    from ivr_b200 import frame_filter as ff
+    for name, case in chain_golden["cases"].items():
+        x = chain_golden["arrays"][name]
+        if name.startswith("vff"):
+            got = ff.extract_unique_frames_rule(x, threshold=case["threshold"])
+        else:
+            got = ff.temporal_window_filter(x, threshold=case["threshold"], temporal_window=case["temporal_window"])
+        assert list(got) == case["kept"], name

@@ -301,3 +301,18 @@ def test_reference_copy_is_unmodified():
         orig = os.path.join("/root/reference", name)
         if os.path.isfile(orig):
             assert hashlib.sha256(open(orig, "rb").read()).hexdigest() == digest, name
+
+
+def test_inline_keep_chain_rules_match_the_reference(chain_golden):
+    """The last-kept rule of video_frame_filter.extract_unique_frames (run as it is, decoder / model stubbed) and
+    Phase 4 of filter_research_update (its statements executed from the parsed source): the restatements reproduce the
+    reference's kept frames exactly."""
+    from oracle import dedup as od
+    for name, case in chain_golden["cases"].items():
+        x = list(chain_golden["arrays"][name])
+        if name.startswith("vff"):
+            got = od.extract_unique_rule(x, case["threshold"])
+        else:
+            got = od.temporal_window_filter(x, case["threshold"], case["temporal_window"])
+        assert got == case["kept"], name
+        assert 0.1 * len(x) < len(got) < 0.95 * len(x)              # the rule really dropped and really kept frames
