@@ -50,7 +50,7 @@ extern "C" {
 
 /* search path selector for ivr_index_search*(): */
 #define IVR_PATH_AUTO    0
-#define IVR_PATH_STREAM  1    /* K3: SIMT streaming, <= 4 queries per pass, HBM-bound (auto: nq <= 2) */
+#define IVR_PATH_STREAM  1    /* K3: SIMT streaming, <= 4 queries per pass, HBM-bound (auto: nq == 1) */
 #define IVR_PATH_MMA     2    /* K1+K2: tcgen05/TMEM batched GEMM with fused top-k epilogue   */
 
 typedef struct ivr_index ivr_index;

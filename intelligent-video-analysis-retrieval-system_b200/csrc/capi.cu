@@ -331,18 +331,18 @@ __global__ void fill_empty_kernel(float* D, int64_t* I, int64_t n) {
 
 namespace ivr {
 
-// Which kernel family serves (nq, k) on this index.  IVR_PATH_AUTO: one or two queries stream on the SIMT kernel
-// (measured after the one-launch merge, 1 M .. 10 M rows, 512 / 768 dims: two queries 0.27 / 0.68 / 2.49 ms streaming
-// vs 0.35 / 0.69 / 2.64 ms on the small-batch tcgen05 kernel; four queries 0.43 / 1.32 / 4.6 vs 0.36 / 0.69 / 2.6);
-// from three queries up the tcgen05 kernels win -- the small-batch kernel wherever its resident query tile fits (any
-// dimension), the batched kernels up to 1024 dims; shapes neither tcgen05 kernel fits (e.g. dim > 1024 with a large
-// batch) stream.
+// Which kernel family serves (nq, k) on this index.  IVR_PATH_AUTO: ONE query streams on the SIMT kernel; from two
+// queries up the tcgen05 kernels win -- the small-batch kernel wherever its resident query tile fits (any dimension),
+// the batched kernels up to 1024 dims.  (Two queries on the streaming kernel are shared-memory bound: 0.27 / 0.79 /
+// 2.08 / 17.9 ms at 1 / 3 / 10 / 100 M x 512 rows against 0.26 / 0.60 / 1.75 / 14.8 ms on the small-batch kernel,
+// which serves small shards in its one-launch dump mode.)  Shapes neither tcgen05 kernel fits (e.g. dim > 1024 with a
+// large batch) stream.
 static int choose_path(const ivr_index* idx, int64_t nq, int k, int path) {
     const bool small_ok = mma_small_supported(idx, nq, k), big_ok = mma_supported(idx, nq, k);
     if (path == IVR_PATH_AUTO) {
         // IVR_AUTO_STREAM_MAX_NQ: tuning knob (measurements only) -- largest batch the streaming kernel serves
         const char* e = getenv("IVR_AUTO_STREAM_MAX_NQ");
-        const int64_t stream_max = (e && *e) ? atoi(e) : 2;
+        const int64_t stream_max = (e && *e) ? atoi(e) : 1;
         if (nq <= stream_max) return IVR_PATH_STREAM;
         return (small_ok || big_ok) ? IVR_PATH_MMA : IVR_PATH_STREAM;
     }

@@ -241,7 +241,7 @@ def test_small_kernel_ties_and_duplicates(small_kernel):
 def test_auto_mode_uses_the_small_kernel_for_small_batches():
     xb = synth.clip_like(50_000, 512, seed=96, n_centres=128)
     idx, ref = build(xb)
-    for nq, kern in [(1, "search_stream_kernel"), (2, "search_stream_kernel"), (3, "search_mma_small_kernel"),
+    for nq, kern in [(1, "search_stream_kernel"), (2, "search_mma_small_kernel"), (3, "search_mma_small_kernel"),
                      (16, "search_mma_small_kernel"), (64, "search_mma_small_kernel"), (300, "search_mma_kernel")]:
         xq = synth.clip_like(nq, 512, seed=97 + nq, n_centres=128)
         check(idx, ref, xq, 100, path=0)
@@ -443,7 +443,7 @@ def test_dims_beyond_1024_pick_a_kernel_that_fits(d, nq):
     idx, ref = build(xb)
     check(idx, ref, xq, 20, path=0)
     tile_fits = ((nq + 15) // 16 * 16) * ((d + 63) // 64 * 64) * 2 <= 128 * 1024     # resident query tile <= 128 KB
-    small_fits = 3 <= nq and tile_fits                               # one or two queries stream on the SIMT kernel
+    small_fits = 2 <= nq and tile_fits                               # one query streams on the SIMT kernel
     t = idx.last_timing()
     assert t["kernel"] == ("search_mma_small_kernel" if small_fits else "search_stream_kernel"), t
     if tile_fits:
