@@ -848,8 +848,10 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const int64_t nq_pad = static_cast<int64_t>(tq) * mq;
     const int tile_rows = xres ? xres_tile_rows(idx) : kTileN;     // both phases use the same tile size
     const int64_t nt = (idx->ntotal + tile_rows - 1) / tile_rows;
-    // Launch boundaries (in row tiles).  The first launch covers a small prefix (IVR_MMA_PHASE0_ROWS, 32k
-    // rows), every further one IVR_MMA_PHASE_RATIO (16) times the rows seen so far, the last one the rest:
+    // Launch boundaries (in row tiles).  The first launch covers a small prefix (IVR_MMA_PHASE0_ROWS, 8 k rows:
+    // measured against 2 k .. 32 k on 100 k .. 100 M rows -- config A 0.65 -> 0.50 ms, 1 M x 4096 queries 5.0 -> 4.2 ms,
+    // neutral from 10 M rows up; profiles/r2_phase0_rows.txt), every further one IVR_MMA_PHASE_RATIO (16) times the
+    // rows seen so far, the last one the rest:
     // a launch admits ~k * ratio candidates per query instead of re-learning its thresholds in every list.
     constexpr int kMaxPhases = 6;
     int64_t bounds[kMaxPhases + 1] = {0};
@@ -859,7 +861,7 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         // its thresholds only improve at launch boundaries: it gets more of them (measured, 10 M x 4096 queries:
         // 34.0 ms at ratio 8 vs 35.5 ms at 16; the query-tile-resident kernel prefers 16: 8.4 vs 8.9 ms at 1024 queries)
         const int64_t ratio = std::max(2, env_int("IVR_MMA_PHASE_RATIO", xres ? 8 : 16));
-        int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 32768) / tile_rows);
+        int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 8192) / tile_rows);
         while (n_phases < kMaxPhases - 1 && b * 2 <= nt) {         // a boundary must leave at least as much for later
             bounds[++n_phases] = b;
             b *= ratio;
