@@ -407,7 +407,7 @@ struct XresParams {
     int       skip_epilogue;   // debug/perf probe: drain nothing (results are garbage)
 };
 
-// TN = rows per tile: 256 for dpad <= 512, 192 for dpad <= 768, 128 for dpad <= 1024 (resident tile <= 144 KB per CTA).
+// TN = rows per tile: 256 for dpad <= 512, 224 (or 192) for dpad <= 768, 128 (or 160) for dpad <= 1024.
 template <int E, int TN>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
@@ -582,11 +582,14 @@ search_mma_xres_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             for (int c = 0; c < (IVR_SKIP_EPI(p) == 1 ? 0 : TN / 32); c += 2) {
                 make_room();
                 tmem_wait_ld(va);
-                tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                const bool pair = (TN / 32) % 2 == 0 || c + 1 < TN / 32;    // TN = 224: seven chunks, the last one alone
+                if (pair) tmem_ld_32x32(taddr + (c + 1) * 32, vb);
                 process_chunk(va, c, row0, nvalid);
-                tmem_wait_ld(vb);
-                if (c + 2 < TN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                process_chunk(vb, c + 1, row0, nvalid);
+                if (pair) {
+                    tmem_wait_ld(vb);
+                    if (c + 2 < TN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                    process_chunk(vb, c + 1, row0, nvalid);
+                }
             }
             p.counts[idx] = cnt;
             // the same query comes back when the next row tile is swept; when tq is odd the prefetched
@@ -738,7 +741,14 @@ static int plan_qres(const ivr_index* idx, int cg, int64_t nq, int k, int64_t ti
 // rows per resident tile: the largest UMMA N whose half tile (N/2 rows x dpad fp16 per CTA) leaves room for the
 // query ring -- 256 up to 512 dims, 192 up to 768 (N = 128 costs 1.5x the shared-memory operand traffic per
 // FLOP: measured 926 TFLOP/s pipeline-only at 768 dims), 128 up to 1024
-static int xres_tile_rows(const ivr_index* idx) { return idx->dpad <= 512 ? 256 : (idx->dpad <= 768 ? 192 : 128); }
+static int xres_tile_rows(const ivr_index* idx) {
+    if (idx->dpad <= 512) return 256;
+    // 768 dims: N = 224 (168 KB resident per CTA, 3-stage query ring) beats N = 192 (144 KB, 5 stages): 10 M x 768 x
+    // 4096 queries 56.7 -> 51.8 ms, x 16384: 219 -> 200 ms (the wider tile reads less shared memory per FLOP)
+    if (idx->dpad <= 768) { const int t = env_int("IVR_XRES_TN_768", 224); return (t == 192 || t == 256) ? t : 224; }
+    // 1024 dims: N = 160 (160 KB resident, 4 stages) beats N = 128 (128 KB, 6 stages): 5 M x 1024 x 4096 queries 47.8 -> 42.9 ms
+    { const int t = env_int("IVR_XRES_TN_1024", 160); return (t == 128 || t == 192) ? t : 160; }
+}
 
 static int plan_xres(const ivr_index* idx, int64_t nq, int k, int64_t tile0, int64_t nt, Plan* pl) {
     constexpr int cg = 2;
@@ -807,6 +817,10 @@ static int run_plan(Plan& pl, const CUtensorMap& tmq, const CUtensorMap& tmx, ui
                                         : launch_cluster(search_mma_xres_kernel<0, 256>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         else if (p.tn == 192) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 192>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
                                              : launch_cluster(search_mma_xres_kernel<0, 192>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        else if (p.tn == 224) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 224>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                             : launch_cluster(search_mma_xres_kernel<0, 224>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
+        else if (p.tn == 160) rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 160>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
+                                             : launch_cluster(search_mma_xres_kernel<0, 160>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         else             rc = pl.E == 8 ? launch_cluster(search_mma_xres_kernel<8, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st)
                                         : launch_cluster(search_mma_xres_kernel<0, 128>, tmq, tmx, p, pl.grid, 2, pl.smem, st);
         IVR_TRY(rc);
