@@ -420,3 +420,33 @@ def test_rvdb_reader_on_a_spec_built_container(tmp_path):
         fh.write(b"\x02")
     with pytest.raises(rr.RvdbFormatError, match="superblock version 2"):
         rr.Hdf5File(path)
+
+
+def test_bench_reference_arm_runs_on_the_host_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver launches beside ours): one JSON line with the contract keys,
+    the reference's own FAISSRetriever path when oracle/_ref (or /root/reference) is present, every host core in use
+    even when the launcher exported OMP_NUM_THREADS=1, and nothing printed by non-zero ranks."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+           "--rows", "500000", "--nq", "64", "--cpu-sample-rows", "20000", "--cpu-sample-queries", "8"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 2 and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["rows"] == 500000 and line["config"]["nq"] == 64 and "workload" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["value"] == line["value"] and cb["kind"] in ("reference", "port") and "sample" in cb
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count()
+    assert cb["cores"] == cores
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        assert cb["kind"] == "reference" and cb["raw_flat_search"]["kind"] == "port"
+    other = subprocess.run(cmd, env=dict(env, RANK="1"), capture_output=True, text=True, timeout=600)
+    assert other.returncode == 0 and other.stdout.strip() == ""
