@@ -16,7 +16,7 @@
 // topk_merge.cu fold the 2368 lists in ONE launch (merge_select_kernel).
 //
 // Algorithmic HBM traffic: ntotal * dpad * 2 bytes per pass.
-#include "merge_select.cuh"
+#include "index.cuh"
 
 namespace ivr {
 
@@ -27,26 +27,14 @@ constexpr int kStreamMaxNq   = 4;
 constexpr int kRowsPerStep   = 4;              // 8 lanes per row
 constexpr int kUnroll        = 2;              // steps in flight
 
-// The merge, fused into the tail of the kernel: the LAST CTA to finish (ticket) folds the per-warp lists of every query
-// of this pass with select_merge_block (merge_select.cuh) and writes the final result -- a search is ONE launch.
-struct StreamTail {
-    int        enabled;      // 0: leave the lists to a separate merge launch (k above the select merge's range)
-    int        kpad;
-    float*     D;            // outputs of this pass ([nq_real, k]); D == nullptr: packed keys go to I
-    int64_t*   I;
-    int64_t    id_offset;
-    uint64_t*  pool;         // [NQ][kSelectPoolCap]
-    int*       state;        // [kStreamMaxNq] pool counters, [kStreamMaxNq] select tickets, [1] kernel ticket: all zero between calls
-};
-
 template <int NQ, int DCH, int E>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
                      const float* __restrict__ q,      // [nq_real, dim] fp32, as the caller passed them
                      int dim, int nq_real,
                      int k, int C, uint64_t* __restrict__ lists, int* __restrict__ counts,
-                     uint32_t* __restrict__ maxima, const StreamTail tail) {
-    extern __shared__ __align__(16) float s_q[];       // NQ * dpad floats; re-used as the merge's key buffer in the tail
+                     uint32_t* __restrict__ maxima) {
+    extern __shared__ float s_q[];                     // NQ * dpad
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rgrp = lane >> 3;
     const int nch = (DCH > 0) ? DCH : dpad / 64;       // 64-element chunks per row
@@ -169,36 +157,12 @@ search_stream_kernel(const __half* __restrict__ rows, int64_t n_rows, int dpad,
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) { counts[gw * NQ + i] = cnt[i]; maxima[gw * NQ + i] = mx; }
     }
-    if (!tail.enabled) return;
-    // ---- fused merge: the last CTA to get here folds all lists ----
-    __shared__ SelectShared ss;
-    __shared__ int s_is_last;
-    __threadfence();
-    __syncthreads();                                   // every warp of this CTA has published its lists; s_q is dead
-    if (threadIdx.x == 0) s_is_last = (atomicAdd(tail.state + 2 * kStreamMaxNq, 1) == static_cast<int>(gridDim.x) - 1);
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    MergeIn in{};
-    in.entries = lists; in.counts = counts;
-    in.list_stride = static_cast<int64_t>(NQ) * C; in.q_stride = C;
-    in.cnt_list_stride = NQ; in.cnt_q_stride = 1;
-    in.n_lists = static_cast<int>(nw);
-    MergeOut out{};
-    out.D = tail.D; out.I = tail.I; out.id_offset = tail.id_offset; out.nq = nq_real;
-    SelectArgs sa{};
-    sa.maxima = maxima; sa.tmax = maxima; sa.t_stride_g = NQ; sa.t_stride_q = 1; sa.n_t = static_cast<int>(nw);
-    sa.pool = tail.pool; sa.pool_cnt = tail.state; sa.ticket = tail.state + kStreamMaxNq; sa.pool_cap = kSelectPoolCap;
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q);
-    for (int qi = 0; qi < nq_real; ++qi) select_merge_block(in, out, sa, k, tail.kpad, qi, 0, 1, s_keys, ss);
-    if (threadIdx.x == 0) tail.state[2 * kStreamMaxNq] = 0;
 }
 
 template <int NQ, int E>
 static int launch_stream(ivr_index* idx, const float* q, int nq_real, int k, int C, uint64_t* lists, int* counts,
-                         uint32_t* maxima, const StreamTail& tail, int grid, cudaStream_t st) {
-    size_t smem = static_cast<size_t>(NQ) * idx->dpad * sizeof(float);
-    if (tail.enabled) smem = std::max(smem, static_cast<size_t>(std::max(tail.kpad, kSelectPoolCap)) * sizeof(uint64_t));
+                         uint32_t* maxima, int grid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(NQ) * idx->dpad * sizeof(float);
     const int dch = idx->dpad / 64;
 #define IVR_LAUNCH_STREAM(DCH)                                                                     \
     do {                                                                                           \
@@ -207,7 +171,7 @@ static int launch_stream(ivr_index* idx, const float* q, int nq_real, int k, int
             IVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                           static_cast<int>(smem)));                                \
         kern<<<grid, kStreamThreads, smem, st>>>(idx->rows, idx->ntotal, idx->dpad, q, idx->dim,   \
-                                                 nq_real, k, C, lists, counts, maxima, tail);      \
+                                                 nq_real, k, C, lists, counts, maxima);            \
     } while (0)
     switch (dch) {
         case 8:  IVR_LAUNCH_STREAM(8);  break;     // 512  (CLIP ViT-B/32)
@@ -221,11 +185,11 @@ static int launch_stream(ivr_index* idx, const float* q, int nq_real, int k, int
 
 template <int E>
 static int launch_stream_nq(ivr_index* idx, int nq, int nq_real, const float* q, int k, int C, uint64_t* lists,
-                            int* counts, uint32_t* maxima, const StreamTail& tail, int grid, cudaStream_t st) {
+                            int* counts, uint32_t* maxima, int grid, cudaStream_t st) {
     switch (nq) {                                  // nq == 3 runs as 4 with a zero query
-        case 1: return launch_stream<1, E>(idx, q, nq_real, k, C, lists, counts, maxima, tail, grid, st);
-        case 2: return launch_stream<2, E>(idx, q, nq_real, k, C, lists, counts, maxima, tail, grid, st);
-        default: return launch_stream<4, E>(idx, q, nq_real, k, C, lists, counts, maxima, tail, grid, st);
+        case 1: return launch_stream<1, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
+        case 2: return launch_stream<2, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
+        default: return launch_stream<4, E>(idx, q, nq_real, k, C, lists, counts, maxima, grid, st);
     }
 }
 
@@ -254,34 +218,31 @@ int search_stream(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* 
     int* tmp_counts = counts + n_lists * kStreamMaxNq;
     uint32_t* maxima = reinterpret_cast<uint32_t*>(ws + o_m);
     uint64_t* pool = reinterpret_cast<uint64_t*>(ws + o_p);
-    int* merge_state = idx->sel_state;                        // pool counters, select tickets, kernel ticket: zero between calls
+    int* merge_state = idx->sel_state;                        // [kStreamMaxNq] pool counters, [kStreamMaxNq] tickets: zero between calls
 
     for (int64_t q0 = 0; q0 < nq; q0 += kStreamMaxNq) {
         const int b_real = static_cast<int>(nq - q0 < kStreamMaxNq ? nq - q0 : kStreamMaxNq);
         const int b = (b_real == 3) ? 4 : b_real;             // kernel batch (3 is padded to 4)
         if (idx->timing && q0 == 0) { cudaEventRecord(idx->ev[4], st); cudaEventRecord(idx->ev[5], st); cudaEventRecord(idx->ev[0], st); }
-        StreamTail tail{};
-        tail.enabled = select ? 1 : 0;
-        tail.kpad = 2; while (tail.kpad < k) tail.kpad <<= 1;
-        tail.D = D_dev ? D_dev + q0 * k : nullptr; tail.I = I_dev + q0 * k; tail.id_offset = id_offset;
-        tail.pool = pool; tail.state = merge_state;
         int rc;
         switch (kcap) {
-            case 128: rc = launch_stream_nq<8>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, tail, grid, st); break;   // k <= 128: register sort
-            default:  rc = launch_stream_nq<0>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, tail, grid, st); break;   // larger k: in-memory sort
+            case 128: rc = launch_stream_nq<8>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, grid, st); break;   // k <= 128: register sort
+            default:  rc = launch_stream_nq<0>(idx, b, b_real, q_dev + q0 * idx->dim, k, C, lists, counts, maxima, grid, st); break;   // larger k: in-memory sort
         }
         IVR_TRY(rc);
         idx->launches[0]++;
         if (idx->timing && q0 == 0) { cudaEventRecord(idx->ev[1], st); cudaEventRecord(idx->ev[2], st); }
-        if (!select) {                                 // k above the select merge's range: exact radix levels in their own launches
-            MergeIn in{};
-            in.entries = lists; in.counts = counts;
-            in.list_stride = static_cast<int64_t>(b) * C; in.q_stride = C;
-            in.cnt_list_stride = b; in.cnt_q_stride = 1;
-            in.n_lists = static_cast<int>(n_lists); in.fixed_count = 0;
+        MergeIn in{};
+        in.entries = lists; in.counts = counts;
+        in.list_stride = static_cast<int64_t>(b) * C; in.q_stride = C;
+        in.cnt_list_stride = b; in.cnt_q_stride = 1;
+        in.n_lists = static_cast<int>(n_lists); in.fixed_count = 0;
+        if (select)
+            IVR_TRY(merge_select_final(in, maxima, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset,
+                                       pool, merge_state, merge_state + kStreamMaxNq, idx->sm_count, st, &idx->launches[1]));
+        else
             IVR_TRY(merge_lists_final(in, b_real, k, D_dev ? D_dev + q0 * k : nullptr, I_dev + q0 * k, id_offset, tmp,
                                       tmp_counts, st, &idx->launches[1]));
-        }
         if (idx->timing && q0 == 0) cudaEventRecord(idx->ev[3], st);
     }
     if (idx->timing) idx->ev_valid[0] = idx->ev_valid[1] = idx->ev_valid[2] = true;

@@ -8,15 +8,159 @@
 // shared-memory histogram) finds the k-th largest key exactly, the k survivors
 // are gathered into shared memory and bitonic-sorted.  Integer-exact; ties on
 // score resolve to the lower row id because the id is part of the key.
-#include "merge_select.cuh"
+#include "index.cuh"
 
 #include <algorithm>
 
 namespace ivr {
 
+constexpr int kMergeThreads = 256;
 constexpr int kMergeFanIn   = 64;     // lists folded by one CTA in a non-final level
 
 static int kpad_for(int k) { int p = 2; while (p < k) p <<= 1; return p; }
+
+struct MergeOut {
+    float*    D;            // final
+    int64_t*  I;
+    int64_t   id_offset;
+    const float* q_scale;   // final: per-query score multiplier (nullptr = 1)
+    uint64_t* entries;      // non-final: [groups, nq, k]
+    int*      counts;       // non-final: [groups, nq]
+    int64_t   nq;
+};
+
+template <typename F>
+__device__ __forceinline__ void for_each_key(const MergeIn& in, int64_t q, int l0, int l1, F&& f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (in.dense) {                                  // materialised scores: rows l * dense_len + i
+        const float* base = in.dense + q * in.dense_q_stride;
+        for (int l = l0 + warp; l < l1; l += nwarps)
+            for (int i = lane; i < in.dense_len; i += 32) {
+                const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                if (row < in.dense_rows) f(make_key(base[row], static_cast<uint32_t>(row)));
+            }
+        return;
+    }
+    for (int l = l0 + warp; l < l1; l += nwarps) {
+        const int cnt = in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride]
+                                  : in.fixed_count;
+        const uint64_t* base = in.entries + l * in.list_stride +
+                               (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+        const int es = in.interleave ? 32 : 1;
+        for (int i = lane; i < cnt; i += 32) {
+            uint64_t key = base[static_cast<int64_t>(i) * es];
+            if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+            if (key != 0ull) f(key);
+        }
+    }
+}
+
+// shared-memory bitonic sort, DESCENDING, of n (a power of two) keys; ends with a barrier
+__device__ __forceinline__ void block_bitonic_desc(uint64_t* s_keys, int n) {
+    for (int s = 2; s <= n; s <<= 1) {
+        for (int t = s >> 1; t > 0; t >>= 1) {
+            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (t - 1));
+                const int hi = lo + t;
+                const bool desc = (lo & s) == 0;
+                const uint64_t a = s_keys[lo], b = s_keys[hi];
+                if ((a < b) == desc) { s_keys[lo] = b; s_keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct MergeShared {
+    int      hist[256];
+    uint64_t prefix, mask;
+    int      remaining, done, n, neq, total;
+};
+
+// Block-level exact selection: the (at most) k largest keys of lists [l0, l1) of query q, sorted descending in
+// s_keys[0 .. kpad) (0-padded).  Returns the number of valid entries.  MSB-first 8-bit radix select on the 64-bit
+// keys, then a shared-memory bitonic sort.  Every thread of the block must call it.
+__device__ int block_select_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
+                                 MergeShared& sh) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh.total = 0; sh.n = 0; sh.neq = 0; sh.prefix = 0; sh.mask = 0; sh.remaining = k; sh.done = 0; }
+    for (int i = tid; i < kpad; i += blockDim.x) s_keys[i] = 0ull;
+    __syncthreads();
+
+    {   // total number of real candidates
+        int local = 0;
+        for_each_key(in, q, l0, l1, [&](uint64_t) { ++local; });
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((tid & 31) == 0 && local) atomicAdd(&sh.total, local);
+    }
+    __syncthreads();
+    const int total = sh.total;
+
+    if (total <= k) {
+        for_each_key(in, q, l0, l1, [&](uint64_t key) { s_keys[atomicAdd(&sh.n, 1)] = key; });
+    } else {
+        uint64_t prefix = 0, mask = 0;
+        int remaining = k;
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            for (int i = tid; i < 256; i += blockDim.x) sh.hist[i] = 0;
+            __syncthreads();
+            for_each_key(in, q, l0, l1, [&](uint64_t key) {
+                if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & 0xff], 1);
+            });
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, b = 255;
+                for (; b > 0; --b) {
+                    const int c = sh.hist[b];
+                    if (cum + c >= remaining) break;
+                    cum += c;
+                }
+                sh.remaining = remaining - cum;
+                sh.prefix = prefix | (static_cast<uint64_t>(b) << shift);
+                sh.mask = mask | (0xffull << shift);
+                sh.done = (sh.hist[b] == remaining - cum);   // the whole bin is needed: stop early
+            }
+            __syncthreads();
+            prefix = sh.prefix; mask = sh.mask; remaining = sh.remaining;
+            if (sh.done) break;
+        }
+        for_each_key(in, q, l0, l1, [&](uint64_t key) {
+            const uint64_t km = key & mask;
+            if (km > prefix) {
+                s_keys[atomicAdd(&sh.n, 1)] = key;
+            } else if (km == prefix) {
+                const int e = atomicAdd(&sh.neq, 1);
+                if (e < remaining) s_keys[k - remaining + e] = key;   // tail slots, disjoint from the > slots
+            }
+        });
+    }
+    __syncthreads();
+    block_bitonic_desc(s_keys, kpad);
+    return min(total, k);
+}
+
+// final output of one query from its sorted keys: (D, I) rows, or packed keys when D == nullptr
+__device__ __forceinline__ void write_final(const MergeOut& out, int64_t q, int k, const uint64_t* s_keys, int nvalid) {
+    const int tid = threadIdx.x;
+    const float scale = out.q_scale ? out.q_scale[q] : 1.0f;
+    if (out.D == nullptr) {
+        // packed-key output for the cross-shard exchange: final score, 32-bit GLOBAL row id, 0 = padding
+        uint64_t* K = reinterpret_cast<uint64_t*>(out.I);
+        const uint32_t off = static_cast<uint32_t>(out.id_offset);
+        for (int i = tid; i < k; i += blockDim.x) {
+            const uint64_t key = s_keys[i];
+            K[q * k + i] = (i < nvalid) ? make_key(key_score(key) * scale, key_row(key) + off) : 0ull;
+        }
+        return;
+    }
+    for (int i = tid; i < k; i += blockDim.x) {
+        const uint64_t key = s_keys[i];
+        const bool ok = i < nvalid;
+        out.D[q * k + i] = ok ? key_score(key) * scale : -3.402823466e+38f;
+        out.I[q * k + i] = ok ? static_cast<int64_t>(key_row(key)) + out.id_offset : -1;
+    }
+}
 
 template <bool FINAL>
 __global__ void __launch_bounds__(kMergeThreads)
@@ -38,12 +182,151 @@ merge_kernel(MergeIn in, MergeOut out, int lists_per_group, int k, int kpad) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// One-launch merge for MANY short lists (the streaming kernel leaves 2368 per-warp lists per query).
+//
+// Bound from the list maxima: the k-th largest of the per-list MAXIMUM scores, T, is reached by k distinct rows, so the
+// final k-th best is >= T and every row of the final top-k has score >= T.  The rows are dealt to the warps round-robin
+// (search_stream.cu), so the best rows sit in different lists and T lands within a few ranks of the true k-th best: only
+// ~k of the ~10^5 .. 10^6 listed candidates survive the filter "score >= T".
+//   1. every CTA finds T from the maxima (32-bit radix select in shared memory; redundant but parallel and L2-fed);
+//   2. the CTAs split the lists and append the survivors to one pool per query (warp-aggregated atomic);
+//   3. the LAST CTA to finish (ticket) sorts the pool and writes the result.  If the pool overflowed (rows clustered
+//      in few lists, massive ties) it falls back to the exact radix select over all lists -- slow but always correct.
+// The ticket and the pool counter are reset by the last CTA: self-cleaning between calls (zeroed once by the caller).
+// ---------------------------------------------------------------------------
+struct SelectArgs {
+    const uint32_t* maxima;     // [n_lists * cnt_list_stride ...] ordered-score maximum of every list (same strides as counts)
+    // the values the bound T is searched in: maximum g of query q at tmax[g * t_stride_g + q * t_stride_q], g < n_t.
+    // Either the list maxima themselves, or the maxima of <= 1024 GROUPS of consecutive lists (dense mode: ~10^4 .. 10^5
+    // tiles per query would make the redundant per-CTA search the dominant cost; ~1000 groups bound just as tightly).
+    const uint32_t* tmax;
+    int64_t   t_stride_g, t_stride_q;
+    int       n_t;
+    uint64_t* pool;             // [nq][pool_cap]
+    int*      pool_cnt;         // [nq]
+    int*      ticket;           // [nq]
+    int       pool_cap;         // power of two
+};
+
 __global__ void __launch_bounds__(kMergeThreads)
 merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
     extern __shared__ uint64_t s_keys[];               // max(kpad, pool_cap)
-    __shared__ SelectShared ss;
-    select_merge_block(in, out, sa, k, kpad, blockIdx.y, blockIdx.x, gridDim.x, s_keys, ss);
+    __shared__ MergeShared sh;
+    __shared__ uint32_t s_T;
+    __shared__ int s_last;
+    const int64_t q = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int M = in.n_lists;
+
+    // ---- 1. T = k-th largest (group) maximum (0 when fewer than k of them are set: admit everything) ----
+    {
+        uint32_t prefix = 0, mask = 0;
+        int remaining = k;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int i = tid; i < 256; i += blockDim.x) sh.hist[i] = 0;
+            __syncthreads();
+            for (int g = tid; g < sa.n_t; g += blockDim.x) {
+                const uint32_t v = sa.tmax[g * sa.t_stride_g + q * sa.t_stride_q];
+                if ((v & mask) == prefix) atomicAdd(&sh.hist[(v >> shift) & 0xff], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {                             // warp-parallel scan from the top bin down
+                int cum_before = 0, found = -1, rem_after = remaining;
+                for (int base = 224; base >= 0 && found < 0; base -= 32) {
+                    const int c = sh.hist[base + 31 - lane];             // lane 0 holds the highest bin of the group
+                    int incl = c;
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    const unsigned hit = __ballot_sync(0xffffffffu, cum_before + incl >= remaining);
+                    if (hit) {
+                        const int l0 = __ffs(hit) - 1;
+                        found = base + 31 - l0;
+                        rem_after = remaining - (cum_before + __shfl_sync(0xffffffffu, incl - c, l0));
+                    }
+                    cum_before += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) {
+                    if (found < 0) { sh.done = 2; }      // fewer than `remaining` maxima match: not enough lists
+                    else {
+                        sh.prefix = prefix | (static_cast<uint32_t>(found) << shift);
+                        sh.mask = mask | (0xffu << shift);
+                        sh.remaining = rem_after;
+                        sh.done = 0;
+                    }
+                }
+            }
+            __syncthreads();
+            if (sh.done == 2) break;
+            prefix = static_cast<uint32_t>(sh.prefix); mask = static_cast<uint32_t>(sh.mask); remaining = sh.remaining;
+        }
+        if (tid == 0) s_T = (sh.done == 2) ? 0u : prefix;
+        __syncthreads();
+    }
+    const uint32_t T = s_T;
+
+    // ---- 2. filter this CTA's share of the lists into the pool ----
+    uint64_t* pool = sa.pool + q * sa.pool_cap;
+    const int per = (M + gridDim.x - 1) / gridDim.x;
+    const int l0 = blockIdx.x * per, l1 = min(l0 + per, M);
+    for (int lb = l0 + warp * 32; lb < l1; lb += nwarps * 32) {      // 32 lists per step: one maximum per lane
+        const int lmine = lb + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, lmine < l1 &&
+                                      sa.maxima[lmine * in.cnt_list_stride + q * in.cnt_q_stride] >= T);
+        while (todo) {                                               // lists with a maximum below T cannot contribute
+            const int l = lb + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int cnt = in.dense ? in.dense_len
+                                     : (in.counts ? in.counts[l * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count);
+            const uint64_t* base = in.dense ? nullptr : in.entries + l * in.list_stride +
+                                   (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+            const int es = in.interleave ? 32 : 1;
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
+                const int i = i0 + lane;
+                uint64_t key = 0ull;
+                if (in.dense) {
+                    const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                    if (i < cnt && row < in.dense_rows)
+                        key = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
+                } else if (i < cnt) {
+                    key = base[static_cast<int64_t>(i) * es];
+                    if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+                }
+                const bool keep = key != 0ull && static_cast<uint32_t>(key >> 32) >= T;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(sa.pool_cnt + q, __popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < sa.pool_cap) pool[pos] = key;
+                }
+            }
+        }
+    }
+
+    // ---- 3. last CTA: sort the pool (or fall back to the exact select) and write the result ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(sa.ticket + q, 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n_pool = *reinterpret_cast<volatile int*>(sa.pool_cnt + q);
+    int nvalid;
+    if (n_pool <= sa.pool_cap) {
+        int np2 = kpad;                                  // sort size: power of two >= max(n_pool, k)
+        while (np2 < n_pool) np2 <<= 1;
+        for (int i = tid; i < np2; i += blockDim.x) s_keys[i] = (i < n_pool) ? __ldcg(pool + i) : 0ull;
+        __syncthreads();
+        block_bitonic_desc(s_keys, np2);
+        nvalid = min(n_pool, k);
+    } else {
+        nvalid = block_select_sort(in, q, 0, M, k, kpad, s_keys, sh);
+    }
+    write_final(out, q, k, s_keys, nvalid);
+    if (tid == 0) { sa.pool_cnt[q] = 0; sa.ticket[q] = 0; }
 }
+
 
 size_t merge_tmp_entries(int n_lists, int64_t nq, int k) {
     // levels shrink by kMergeFanIn; two ping-pong buffers sized for the first level
