@@ -221,15 +221,35 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
 
     // ---- 1. T = k-th largest (group) maximum (0 when fewer than k of them are set: admit everything) ----
     {
+        // the maxima are fetched ONCE, all loads of a thread in flight together (up to 16 per thread = 4096 values:
+        // 2368 lists of the streaming kernel, <= 1024 tile groups in dense mode); the four radix passes then run on
+        // registers -- a dependent global load per value and pass used to be most of this kernel's 21 us
+        constexpr int kMine = 16;
+        uint32_t mine[kMine];
+        const bool in_regs = sa.n_t <= kMine * kMergeThreads;
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < kMine; ++j) {
+                const int g = tid + j * kMergeThreads;
+                mine[j] = (g < sa.n_t) ? sa.tmax[g * sa.t_stride_g + q * sa.t_stride_q] : 0u;
+            }
+        }
         uint32_t prefix = 0, mask = 0;
         int remaining = k;
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
             for (int i = tid; i < 256; i += blockDim.x) sh.hist[i] = 0;
             __syncthreads();
-            for (int g = tid; g < sa.n_t; g += blockDim.x) {
-                const uint32_t v = sa.tmax[g * sa.t_stride_g + q * sa.t_stride_q];
-                if ((v & mask) == prefix) atomicAdd(&sh.hist[(v >> shift) & 0xff], 1);
+            if (in_regs) {
+#pragma unroll
+                for (int j = 0; j < kMine; ++j)
+                    if (tid + j * kMergeThreads < sa.n_t && (mine[j] & mask) == prefix)
+                        atomicAdd(&sh.hist[(mine[j] >> shift) & 0xff], 1);
+            } else {
+                for (int g = tid; g < sa.n_t; g += blockDim.x) {
+                    const uint32_t v = sa.tmax[g * sa.t_stride_g + q * sa.t_stride_q];
+                    if ((v & mask) == prefix) atomicAdd(&sh.hist[(v >> shift) & 0xff], 1);
+                }
             }
             __syncthreads();
             if (warp == 0) {                             // warp-parallel scan from the top bin down
@@ -281,24 +301,31 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
             const uint64_t* base = in.dense ? nullptr : in.entries + l * in.list_stride +
                                    (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
             const int es = in.interleave ? 32 : 1;
-            for (int i0 = 0; i0 < cnt; i0 += 32) {
-                const int i = i0 + lane;
-                uint64_t key = 0ull;
-                if (in.dense) {
-                    const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
-                    if (i < cnt && row < in.dense_rows)
-                        key = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
-                } else if (i < cnt) {
-                    key = base[static_cast<int64_t>(i) * es];
-                    if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+            for (int i0 = 0; i0 < cnt; i0 += 32 * 8) {               // 8 entries per lane in flight: one load latency per 256 entries
+                uint64_t key[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    key[u] = 0ull;
+                    if (in.dense) {
+                        const int64_t row = static_cast<int64_t>(l) * in.dense_len + i;
+                        if (i < cnt && row < in.dense_rows)
+                            key[u] = make_key(in.dense[q * in.dense_q_stride + row], static_cast<uint32_t>(row));
+                    } else if (i < cnt) {
+                        key[u] = base[static_cast<int64_t>(i) * es];
+                        if (in.raw) key[u] = make_key(__uint_as_float(static_cast<uint32_t>(key[u])), static_cast<uint32_t>(key[u] >> 32));
+                    }
                 }
-                const bool keep = key != 0ull && static_cast<uint32_t>(key >> 32) >= T;
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (m) {
-                    int pos = 0;
-                    if (lane == 0) pos = atomicAdd(sa.pool_cnt + q, __popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                    if (keep && pos < sa.pool_cap) pool[pos] = key;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool keep = key[u] != 0ull && static_cast<uint32_t>(key[u] >> 32) >= T;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        int pos = 0;
+                        if (lane == 0) pos = atomicAdd(sa.pool_cnt + q, __popc(m));
+                        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                        if (keep && pos < sa.pool_cap) pool[pos] = key[u];
+                    }
                 }
             }
         }
