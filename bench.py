@@ -644,8 +644,9 @@ def run_ours(args):
                                    else "fallback 1400 / 1590 TFLOP/s",
                     "traffic": measured_traffic(launches["kernel"], n_local, dim, nq, k), "kernel": launches["kernel"],
                     "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
-                    "note": "kernel_ms brackets the whole scoring stage of one search: the short threshold-seeding "
-                            "launches (~3 %), their merges (<0.3 %) and the bulk launch"}
+                    "note": "kernel_ms brackets the whole scoring stage of one search: the short query-tile-resident "
+                            "threshold-seeding launches (<1 %), the merges between launches (<1 %) and the "
+                            "row-tile-resident launches (profiles/r2_launches_bench_n1.csv)"}
     else:
         passes = (nq + 3) // 4
         ach = (float(n_local) * dim * 2) / (k_ms * 1e-3) / 1e9   # events bracket the first pass of a multi-pass search
