@@ -147,7 +147,7 @@ def partition_units(lengths, world_size: int) -> np.ndarray:
 class ShardedFrameFilter:
     """Near-duplicate pruning of many videos on several GPUs: every rank prunes ITS videos (scene split on
     the consecutive cosine inside each video, then the windowed rule inside each scene -- filter.py:142-315)
-    in two kernel passes over one contiguous frame range; videos are never split, so no halo and no
+    with one fused ``ivr_frame_filter`` call per video; videos are never split, so no halo and no
     collective on the data path.  ``gather`` (optional, control plane) collects the kept indices.
 
     ``ops`` is the module providing ``calculate_similarities``, ``detect_scene_transitions``,
@@ -178,6 +178,15 @@ class ShardedFrameFilter:
         lo, hi = self.my_units(video_bounds)
         if lo >= hi:
             return []
+        if hasattr(self.ops, "FrameFilter"):                        # CUDA path: one fused call per video -- the frames cross
+            f = self.ops.FrameFilter(window=self.config["similarity_window_size"],     # PCIe once, scene split and greedy
+                                     threshold=self.config["similarity_threshold"],    # rule run on the device, and a scene
+                                     transition_threshold=self.transition_threshold,   # can never cross a video boundary
+                                     min_scene_length=self.min_scene_length)
+            kept: list = []
+            for vs, ve in video_bounds[lo:hi]:
+                kept.extend((f.apply_filters(embeddings[vs:ve + 1]) + vs).tolist())
+            return kept
         s0, e1 = video_bounds[lo][0], video_bounds[hi - 1][1]
         x = embeddings[s0:e1 + 1]
         sims = self.ops.calculate_similarities(x)                   # one pass over the rank's frames
