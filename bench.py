@@ -73,6 +73,8 @@ def parse_args():
     p.add_argument("--cpu-sample-queries", type=int, default=256)
     p.add_argument("--cpu-dedup-frames", type=int, default=10_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--equal-shards", action="store_true",
+                   help="N > 1: split the rows equally instead of by each GPU's measured scoring rate")
     p.add_argument("--no-extras", action="store_true",
                    help="skip the informational legs (BASELINE configs A, B, C, the production-shaped cell)")
     return p.parse_args()
@@ -526,10 +528,7 @@ def run_ours(args):
     dim, k, nq, n_total = args.dim, args.k, args.nq, args.rows
     if n_total % GEN_CHUNK and n_total > GEN_CHUNK:
         raise SystemExit(f"--rows must be a multiple of {GEN_CHUNK}")
-    n_chunks = max(1, n_total // GEN_CHUNK)
     chunk_rows = n_total if n_total < GEN_CHUNK else GEN_CHUNK
-    c_off = partition_rows(n_chunks, world)                      # shard = whole generation chunks
-    row0, row1 = int(c_off[rank]) * chunk_rows, int(c_off[rank + 1]) * chunk_rows
 
     cen = centres(dim, dev)
     q_host = gen_queries(nq, dim, cen.cpu()).pin_memory()
@@ -540,29 +539,72 @@ def run_ours(args):
     index = ShardedFlatIP(dim, device=local_rank) if world > 1 else None
     local = index.local if index else ivr_b200.IndexFlatIP(dim, device=local_rank)
     local.search_path = args.path
-    local.reserve(row1 - row0)
-    # build the shard + an exact fp32 top-k of the check queries over the SAME rows (the checker)
     torch.backends.cuda.matmul.allow_tf32 = False
-    best_d = torch.full((n_chk, k), -float("inf"), device=dev)
-    best_i = torch.full((n_chk, k), -1, dtype=torch.int64, device=dev)
+
+    def build_shard(row0, row1, check, headroom=1.0):
+        """Rows [row0, row1) of the synthetic matrix (generated chunk by chunk; a rank whose boundary falls inside a
+        chunk keeps its part of it) + when `check`: an exact fp32 top-k of the check queries over the SAME rows."""
+        local.reset()
+        local.reserve(int((row1 - row0) * headroom))
+        bd = torch.full((n_chk, k), -float("inf"), device=dev)
+        bi = torch.full((n_chk, k), -1, dtype=torch.int64, device=dev)
+        for c in range(row0 // chunk_rows, (row1 + chunk_rows - 1) // chunk_rows):
+            x = gen_rows(c, chunk_rows, dim, cen, dev)
+            lo, hi = max(row0, c * chunk_rows), min(row1, (c + 1) * chunk_rows)
+            if hi - lo < chunk_rows:
+                x = x[lo - c * chunk_rows:hi - c * chunk_rows].contiguous()
+            if index:
+                index.add_local(x, row0, n_total)
+            else:
+                local.add(x)
+            if check:
+                s = q_chk @ x.T
+                d_, i_ = torch.topk(s, min(k, x.shape[0]), dim=1)
+                cd, ci = torch.cat([bd, d_], 1), torch.cat([bi, i_ + lo], 1)
+                o = torch.argsort(cd, dim=1, descending=True, stable=True)[:, :k]
+                bd, bi = torch.gather(cd, 1, o), torch.gather(ci, 1, o)
+                del s
+            del x
+        torch.cuda.synchronize()
+        return bd, bi
+
     t_build = time.perf_counter()
-    for c in range(int(c_off[rank]), int(c_off[rank + 1])):
-        x = gen_rows(c, chunk_rows, dim, cen, dev)
-        if index:
-            index.add_local(x, row0, n_total)
-        else:
-            local.add(x)
-        s = q_chk @ x.T
-        d_, i_ = torch.topk(s, min(k, x.shape[0]), dim=1)
-        cd, ci = torch.cat([best_d, d_], 1), torch.cat([best_i, i_ + c * chunk_rows], 1)
-        o = torch.argsort(cd, dim=1, descending=True, stable=True)[:, :k]
-        best_d, best_i = torch.gather(cd, 1, o), torch.gather(ci, 1, o)
-        del x, s
-    torch.cuda.synchronize()
+    off = partition_rows(n_total, world, align=1)
+    balance = None
+    if world > 1 and not args.equal_shards:
+        # GPUs under the same power cap differ by a few per cent, and with the pipelined exchange the job runs at the
+        # pace of the slowest rank's own work: size the shards by MEASURED scoring speed.  Equal shards first, every
+        # rank times its local search, the rates are all-gathered and the matrix is re-partitioned.
+        build_shard(int(off[rank]), int(off[rank + 1]), check=False, headroom=1.06)   # room for a faster GPU's share
+        rate = torch.tensor([index.scoring_rate(q_dev, k, reps=8, warm=4)], device=dev, dtype=torch.float64)
+        rates = [torch.empty_like(rate) for _ in range(world)]
+        dist.all_gather(rates, rate)
+        rates = [float(r.item()) for r in rates]
+        off = partition_rows(n_total, world, weights=rates, align=1024)
+        balance = {"rows_per_ms_equal_shards": [round(r, 1) for r in rates],
+                   "rows_per_rank": [int(off[r + 1] - off[r]) for r in range(world)]}
+    row0, row1 = int(off[rank]), int(off[rank + 1])
+    best_d, best_i = build_shard(row0, row1, check=True)
     t_build = time.perf_counter() - t_build
 
     def search_dev(q):
         return index.search(q, k) if index else local.search_tensor(q, k)
+
+    def run_steps(n):
+        """n searches back to back.  Sharded: two in flight -- the exchange + merge of search i run on the index's
+        side stream while search i+1 is being scored (ShardedFlatIP.search_async); every result is complete and
+        ordered into the timing stream before the closing event."""
+        if not index:
+            for _ in range(n):
+                local.search_tensor(q_dev, k)
+            return
+        prev = None
+        for _ in range(n):
+            h = index.search_async(q_dev, k)
+            if prev is not None:
+                prev.result(copy=False)
+            prev = h
+        prev.result(copy=False)
 
     def barrier():
         if world > 1:
@@ -583,16 +625,14 @@ def run_ours(args):
     del best_d, best_i
 
     # ---- value: whole-job throughput, inputs resident in HBM ---------------------------
-    for _ in range(args.warmup):
-        search_dev(q_dev)
+    run_steps(args.warmup)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        search_dev(q_dev)
+    run_steps(args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -656,28 +696,37 @@ def run_ours(args):
     roofline["kernel_ms_per_rank"] = {"min": min(k_ranks), "max": max(k_ranks), "all": k_ranks}
     per_step_launches = launches["score_launches"] + launches["merge_launches"] + launches["prep_launches"]
     if world > 1:
-        per_step_launches += 1                                   # the key merge after the all-gather
+        per_step_launches += 2 if index.exchange == "peer" else 1   # push kernel + the key merge after the exchange
 
     # ---- e2e: host buffers in, host results out, through the public API ----------------
-    res_d = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    res_i = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     q_np = q_host.numpy()
+    if world > 1:                                                # two steps in flight: device queries + pinned results x2
+        qd2 = [torch.empty_like(q_dev) for _ in range(2)]
+        res2 = [(torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                 torch.empty((nq, k), dtype=torch.int64).pin_memory()) for _ in range(2)]
 
-    def e2e_step():
+    def e2e_steps(n):
+        """Every step: pinned host queries -> device, search, hits -> pinned host memory.  One GPU: the C ABI with HOST
+        pointers (H2D + D2H inside the call).  Sharded: the D2H copies are queued behind the merge on the side
+        stream and the host waits for step i after issuing step i+1 (two steps in flight)."""
         if world == 1:
-            return local.search(q_np, k)                         # C ABI with HOST pointers (H2D + D2H inside)
-        qd = q_host.to(dev, non_blocking=True)
-        D_, I_ = index.search(qd, k)
-        res_d.copy_(D_, non_blocking=True); res_i.copy_(I_, non_blocking=True)
-        torch.cuda.synchronize()
-        return res_d, res_i
+            for _ in range(n):
+                local.search(q_np, k)
+            return
+        prev = None
+        for s_ in range(n):
+            b = s_ % 2
+            qd2[b].copy_(q_host, non_blocking=True)
+            h = index.search_async(qd2[b], k).to_host(*res2[b])
+            if prev is not None:
+                prev.synchronize()
+            prev = h
+        prev.synchronize()
 
-    for _ in range(args.warmup):
-        e2e_step()
+    e2e_steps(args.warmup)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_steps(args.steps)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -697,7 +746,12 @@ def run_ours(args):
                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                "config": workload_config(args),
                "run": {"storage": "fp16 rows, fp32 accumulate", "rows_per_gpu": n_local, "path": path,
-                       "parallelism": f"row-shard x{world} + one all_gather of packed 64-bit keys + k-way merge",
+                       "parallelism": (f"row-shard x{world}" if world > 1 else "one shard") + (
+                           "" if world == 1 else
+                           " + packed 64-bit keys pushed into peer mailboxes over NVLink (stream-ordered arrival wait)"
+                           " + k-way merge; two searches in flight" if index.exchange == "peer" else
+                           " + one all_gather of packed 64-bit keys + k-way merge"),
+                       "exchange": index.exchange if index else None, "shard_balance": balance,
                        "build_s": round(t_build, 2)},
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                        "d2h_bytes_per_step": nq * k * 12},

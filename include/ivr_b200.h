@@ -127,6 +127,37 @@ IVR_API int ivr_topk_merge_device(int device, const float* D_parts, const int64_
 IVR_API int ivr_topk_merge_keys_device(int device, const uint64_t* keys_parts, int n_parts, int64_t nq, int k,
                                float* D_out, int64_t* I_out, void* stream);
 
+/* ---- K7: cross-shard hit exchange over NVLink / NVSwitch peer memory ------------------------
+ * Replaces the "collect every shard's hit list" step of _search_with_remote_index (system.py:1721-1746) for
+ * one process per GPU on one box.  Every rank owns a MAILBOX in its HBM: `slots` regions of [world][capacity]
+ * packed keys (the format of ivr_index_search_keys_device) + one arrival flag per (slot, sender).
+ *   create        allocates and zeroes the mailbox (cudaMalloc, exportable through CUDA IPC)
+ *   ipc_handle    64-byte CUDA IPC handle of my mailbox; the caller exchanges the handles of all ranks
+ *                 (any control-plane channel, e.g. one torch.distributed all-gather at set-up time)
+ *   connect_ipc   maps every peer's mailbox (handles: [world][64] in rank order; my own entry is ignored);
+ *                 IVR_EUNSUPPORTED when a peer cannot be mapped (no P2P / different IPC namespace)
+ *   connect_ptrs  the same with already-mapped device pointers (ranks living in one process)
+ *   push          one kernel: copies my n_entries keys into part `rank` of slot `slot` of EVERY mailbox (16-byte
+ *                 peer stores), fences system-wide, then stores `epoch` into my flag of that slot on every rank
+ *   wait          queues stream memory operations (cuStreamWaitValue32 >=) until all `world` flags of the slot
+ *                 reached `epoch`; no SM is held while waiting
+ *   slot          device pointer of the slot: uint64 [world][n_entries] after a completed wait -- the
+ *                 keys_parts argument of ivr_topk_merge_keys_device
+ * Protocol: search s uses slot s % slots with epoch s / slots + 1; every rank issues push, wait and the merge of
+ * consecutive searches in ONE stream, which makes slot reuse safe without acknowledgements (csrc/exchange.cu). */
+#define IVR_IPC_HANDLE_BYTES 64
+typedef struct ivr_exchange ivr_exchange;
+IVR_API int   ivr_exchange_create(int device, int rank, int world, int slots, int64_t capacity, ivr_exchange** out);
+IVR_API int   ivr_exchange_destroy(ivr_exchange* ex);
+IVR_API void* ivr_exchange_base(ivr_exchange* ex);
+IVR_API int   ivr_exchange_ipc_handle(ivr_exchange* ex, uint8_t* handle);
+IVR_API int   ivr_exchange_connect_ipc(ivr_exchange* ex, const uint8_t* handles);
+IVR_API int   ivr_exchange_connect_ptrs(ivr_exchange* ex, void* const* bases);
+IVR_API int   ivr_exchange_push(ivr_exchange* ex, const uint64_t* keys_dev, int64_t n_entries, int slot,
+                                uint32_t epoch, void* stream);
+IVR_API int   ivr_exchange_wait(ivr_exchange* ex, int slot, uint32_t epoch, void* stream);
+IVR_API const uint64_t* ivr_exchange_slot(ivr_exchange* ex, int slot);
+
 /* Replaces faiss.normalize_L2(x) (unified_index.py:1776): in-place row L2
  * normalisation, zero rows untouched. */
 IVR_API int ivr_normalize_l2(int device, float* x_host, int64_t n, int d);

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libivr_b200.so")
 IVR_OK, IVR_EINVAL, IVR_ENODEVICE, IVR_ECUDA, IVR_ENOMEM, IVR_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 IVR_MAX_K = 2048
 IVR_MAX_WINDOW = 32
+IVR_IPC_HANDLE_BYTES = 64
 PATH_AUTO, PATH_STREAM, PATH_MMA = 0, 1, 2
 
 _c_f32p = C.POINTER(C.c_float)
@@ -55,6 +56,15 @@ PROTOTYPES = {
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ivr_topk_merge_keys_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p]),
+    "ivr_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "ivr_exchange_destroy": (C.c_int, [C.c_void_p]),
+    "ivr_exchange_base": (C.c_void_p, [C.c_void_p]),
+    "ivr_exchange_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ivr_exchange_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ivr_exchange_connect_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ivr_exchange_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_void_p]),
+    "ivr_exchange_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]),
+    "ivr_exchange_slot": (C.c_void_p, [C.c_void_p, C.c_int]),
     "ivr_normalize_l2": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "ivr_normalize_l2_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ivr_consecutive_cosine": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),

@@ -6,12 +6,20 @@ rank r owns global ids ``[offsets[r], offsets[r+1])``.  A search replicates the
 queries, runs the local exact top-k on every GPU with GLOBAL ids
 (``id_offset``) and leaves the hits as PACKED 64-bit keys (score and id in one
 word, 8 bytes per hit -- the form the local search already holds before its
-final unpack), exchanges the ``[nq, k]`` key lists with ONE
-``all_gather_into_tensor`` into a buffer the index owns, and folds them with the
+final unpack), exchanges the ``[nq, k]`` key lists and folds them with the
 on-device k-way merge kernel (``ivr_topk_merge_keys_device``: one launch, no
 scratch, no allocation).  Exactness: the global top-k is a subset of the union
 of the local top-k lists.  The key holds a 32-bit id, so a sharded index is
 limited to 2^32 - 1 rows in total (checked at ``add``).
+
+The exchange (``exchange="peer"``, the default on GPUs with peer access) is our
+own kernel over NVLink peer memory: every rank PUSHES its keys into a mailbox
+in each peer's HBM and raises a flag; the receiver waits with a stream memory
+operation, not with a spinning kernel (``csrc/exchange.cu``).  Push, wait and
+merge run on a side stream, so ``search_async`` lets the scoring of batch i+1
+start while slower peers still finish batch i -- the per-batch straggler wait
+of a collective disappears from the throughput.  ``exchange="nccl"`` keeps the
+ONE ``all_gather_into_tensor`` path (and is what injected CPU back-ends use).
 
 Reference precedent for the semantics: ``_search_with_remote_index``
 concatenates the per-shard hit lists, sorts and truncates (system.py:1721-1746;
@@ -26,9 +34,20 @@ from typing import Callable, Optional
 import numpy as np
 
 
-def partition_rows(n_total: int, world_size: int) -> np.ndarray:
-    """Contiguous balanced partition: offsets[r] = floor(r * n / world)."""
-    return np.array([(r * n_total) // world_size for r in range(world_size + 1)], dtype=np.int64)
+def partition_rows(n_total: int, world_size: int, weights=None, align: int = 1) -> np.ndarray:
+    """Contiguous partition.  Balanced by default: offsets[r] = floor(r * n / world).  With ``weights`` (one
+    positive number per rank, e.g. the scoring rates ``ShardedFlatIP.scoring_rate`` measured: GPUs under the same
+    power cap differ by a few per cent, and with the pipelined exchange throughput is set by the SLOWEST rank's own
+    work) rank r receives a share proportional to its weight; inner boundaries are rounded to ``align`` rows."""
+    if weights is None:
+        return np.array([(r * n_total) // world_size for r in range(world_size + 1)], dtype=np.int64)
+    w = np.asarray(weights, dtype=np.float64)
+    if w.shape != (world_size,) or not np.all(np.isfinite(w)) or np.any(w <= 0):
+        raise ValueError("weights: one positive finite number per rank")
+    cum = np.concatenate([[0.0], np.cumsum(w)]) / w.sum()
+    off = np.rint(cum * n_total / align).astype(np.int64) * align
+    off[0], off[-1] = 0, n_total
+    return np.minimum(np.maximum.accumulate(off), n_total)
 
 
 MAX_SHARDED_ROWS = (1 << 32) - 1          # the exchange key holds a 32-bit global row id
@@ -49,6 +68,80 @@ def _cuda_merge(device: int):
     return merge
 
 
+class _PeerExchange:
+    """The mailbox of ``csrc/exchange.cu`` for one rank (ctypes over ``ivr_exchange_*``)."""
+
+    SLOTS = 2
+
+    def __init__(self, device: int, rank: int, world: int, capacity: int):
+        from . import _native as nat
+        self.nat, self.device, self.rank, self.world, self.capacity = nat, device, rank, world, int(capacity)
+        h = C.c_void_p()
+        nat.check(nat.lib.ivr_exchange_create(device, rank, world, self.SLOTS, self.capacity, C.byref(h)))
+        self.h = h
+
+    def ipc_handle(self) -> bytes:
+        buf = (C.c_uint8 * self.nat.IVR_IPC_HANDLE_BYTES)()
+        self.nat.check(self.nat.lib.ivr_exchange_ipc_handle(self.h, buf))
+        return bytes(buf)
+
+    def base(self) -> int:
+        return int(self.nat.lib.ivr_exchange_base(self.h))
+
+    def connect_ipc(self, handles: bytes) -> None:
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self.nat.check(self.nat.lib.ivr_exchange_connect_ipc(self.h, buf))
+
+    def connect_ptrs(self, bases) -> None:
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(int(b)) for b in bases])
+        self.nat.check(self.nat.lib.ivr_exchange_connect_ptrs(self.h, arr))
+
+    def push(self, keys_ptr: int, n: int, slot: int, epoch: int, stream: int) -> None:
+        self.nat.check(self.nat.lib.ivr_exchange_push(self.h, keys_ptr, n, slot, epoch, stream))
+
+    def wait(self, slot: int, epoch: int, stream: int) -> None:
+        self.nat.check(self.nat.lib.ivr_exchange_wait(self.h, slot, epoch, stream))
+
+    def slot_ptr(self, slot: int) -> int:
+        return int(self.nat.lib.ivr_exchange_slot(self.h, slot))
+
+    def close(self) -> None:
+        if self.h:
+            self.nat.lib.ivr_exchange_destroy(self.h)
+            self.h = None
+
+
+class PendingSearch:
+    """Result of ``ShardedFlatIP.search_async``: the hits exist once the side stream has merged them.
+    ``result()`` orders the CURRENT stream behind that and returns ``(D, I)``; with ``copy=False`` these are the
+    index's own per-slot buffers, valid until two further searches have been issued.  ``to_host`` queues the
+    device-to-host copies behind the merge (no wait on the scoring stream); ``synchronize`` blocks the host."""
+
+    def __init__(self, D, I, done, stream):
+        self.D, self.I, self._done, self._stream = D, I, done, stream
+
+    def result(self, copy: bool = True):
+        import torch
+        if self._done is not None:
+            torch.cuda.current_stream(self.D.device).wait_event(self._done)
+        return (self.D.clone(), self.I.clone()) if copy else (self.D, self.I)
+
+    def to_host(self, D_host, I_host) -> "PendingSearch":
+        import torch
+        if self._stream is None:
+            D_host.copy_(self.D, non_blocking=True); I_host.copy_(self.I, non_blocking=True)
+            self._done = torch.cuda.Event(); self._done.record()
+            return self
+        with torch.cuda.stream(self._stream):
+            D_host.copy_(self.D, non_blocking=True); I_host.copy_(self.I, non_blocking=True)
+            self._done = torch.cuda.Event(); self._done.record(self._stream)
+        return self
+
+    def synchronize(self) -> None:
+        if self._done is not None:
+            self._done.synchronize()
+
+
 class ShardedFlatIP:
     """Exact inner-product index row-sharded over the ranks of a process group.
 
@@ -59,13 +152,15 @@ class ShardedFlatIP:
     """
 
     def __init__(self, d: int, group=None, device: Optional[int] = None,
-                 local_index=None, merge: Optional[Callable] = None):
+                 local_index=None, merge: Optional[Callable] = None, exchange: Optional[str] = None):
+        import os
         import torch.distributed as dist
         self.d = int(d)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        if local_index is None:
+        cuda_backend = local_index is None
+        if cuda_backend:
             from . import _native as nat
             from .faiss_compat import IndexFlatIP
             self.device = nat.default_device() if device is None else device
@@ -79,12 +174,25 @@ class ShardedFlatIP:
         self.ntotal_global = 0
         self._keys = None          # [nq, k] local keys and [world, nq, k] gathered keys, reused across searches
         self._gathered = None
+        # exchange transport: "peer" (mailboxes over NVLink peer memory, pipelined) or "nccl" (one all-gather);
+        # None = IVR_EXCHANGE, else peer for the CUDA back-end (falling back to nccl, on every rank together, when the
+        # mailboxes cannot be mapped) and nccl for injected back-ends
+        want = exchange or (os.environ.get("IVR_EXCHANGE") if cuda_backend else None) or ("peer" if cuda_backend else "nccl")
+        if want not in ("peer", "nccl"):
+            raise ValueError(f"exchange must be 'peer' or 'nccl', got {want!r}")
+        self.exchange = want
+        self._auto_exchange = exchange is None and "IVR_EXCHANGE" not in os.environ
+        self._mail = None          # _PeerExchange, created at the first search (capacity = nq * k, regrown collectively)
+        self._comm = None          # side stream: push -> wait -> merge of consecutive searches, in order
+        self._step = 0
+        self._slots = None         # per slot: keys, D, I, pushed-event
 
     # ---- build ---------------------------------------------------------
-    def add_global(self, x) -> None:
-        """Every rank passes the same [n, d] matrix (or a view of it); each keeps its block."""
+    def add_global(self, x, weights=None) -> None:
+        """Every rank passes the same [n, d] matrix (or a view of it); each keeps its block (``weights``: see
+        ``partition_rows``; the same on every rank)."""
         n = x.shape[0]
-        off = partition_rows(n, self.world)
+        off = partition_rows(n, self.world, weights)
         if self.ntotal_global != 0:
             raise RuntimeError("add_global supports one contiguous build; use add_local to append")
         if n > MAX_SHARDED_ROWS:
@@ -106,22 +214,128 @@ class ShardedFlatIP:
     def ntotal(self) -> int:
         return self.ntotal_global
 
+    def scoring_rate(self, q, k: int, reps: int = 8, warm: int = 3) -> float:
+        """Rows per millisecond THIS rank's GPU scores for the batch ``q`` on its current shard (device-timed, local
+        search only, no exchange).  All-gather the rates and pass them to ``partition_rows`` / ``add_global`` as
+        ``weights`` to size the shards by measured speed."""
+        self.local.set_timing(True)
+        ms = []
+        for i in range(warm + reps):
+            self.local.search_keys_tensor(q, int(k), id_offset=self.id_offset)
+            t = self.local.last_timing()
+            if i >= warm:
+                ms.append(t["score_ms"] + t["merge_ms"] + t["prep_ms"])
+        self.local.set_timing(False)
+        return float(self.local.ntotal) / (sum(ms) / len(ms))
+
     # ---- search --------------------------------------------------------
     def search(self, q, k: int):
         """q: [nq, d] tensor (CUDA for the product path), replicated on every rank.
         Returns (D [nq,k] float32 descending, I [nq,k] int64 global ids) on every rank."""
+        return self.search_async(q, k).result(copy=True)
+
+    def search_async(self, q, k: int) -> PendingSearch:
+        """Queue one search and return at once.  The local scoring runs on the current stream; with the peer
+        exchange the push / arrival wait / merge run on the index's side stream, so the NEXT ``search_async`` starts
+        scoring while this one's exchange is still waiting for slower ranks.  Searches complete in issue order."""
         import torch
         import torch.distributed as dist
         k = int(k)
         if self.world == 1:
-            return self.local.search_tensor(q, k, id_offset=self.id_offset)
+            D, I = self.local.search_tensor(q, k, id_offset=self.id_offset)
+            return PendingSearch(D, I, None, None)
         nq = q.shape[0]
+        if self.exchange == "peer" and nq > 0 and self._ensure_mailbox(nq * k, q.device):
+            return self._search_peer(q, nq, k)
         if self._keys is None or self._keys.shape != (nq, k) or self._keys.device != q.device:
             self._keys = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             self._gathered = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
         self.local.search_keys_tensor(q, k, id_offset=self.id_offset, out=self._keys)
         dist.all_gather_into_tensor(self._gathered.view(self.world * nq, k), self._keys, group=self.group)
-        return self._merge(self._gathered, k)
+        D, I = self._merge(self._gathered, k)
+        return PendingSearch(D, I, None, None)
+
+    # ---- peer-memory exchange (csrc/exchange.cu) ---------------------------
+    def _ensure_mailbox(self, n_entries: int, device) -> bool:
+        """Collective: (re)creates the mailboxes when the payload outgrows them and maps the peers' through CUDA
+        IPC.  Every rank calls it with the same size (queries are replicated).  Returns False -- on every rank --
+        when some rank cannot map a peer and the transport was chosen automatically (then NCCL takes over)."""
+        import torch
+        import torch.distributed as dist
+        if self._mail is not None and n_entries <= self._mail.capacity:
+            return True
+        from . import _native as nat
+        if self._mail is not None:                      # nobody may still be writing into the old mailboxes
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)
+            self._mail.close()
+            self._mail = None
+        mail = _PeerExchange(self.device, self.rank, self.world, n_entries)
+        mine = torch.frombuffer(bytearray(mail.ipc_handle()), dtype=torch.uint8).to(device)
+        allh = torch.empty((self.world, nat.IVR_IPC_HANDLE_BYTES), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        ok = 1
+        try:
+            mail.connect_ipc(allh.cpu().numpy().tobytes())
+        except nat.NativeError:
+            if not self._auto_exchange:
+                raise
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            mail.close()
+            self.exchange = "nccl"
+            return False
+        self._mail = mail
+        self._step = 0
+        self._slots = None
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=device)
+        return True
+
+    def _search_peer(self, q, nq: int, k: int) -> PendingSearch:
+        import torch
+        S = _PeerExchange.SLOTS
+        if self._slots is None or self._slots[0]["keys"].shape != (nq, k) or self._slots[0]["keys"].device != q.device:
+            if self._slots is not None:
+                self._comm.synchronize()
+            self._slots = [{"keys": torch.empty((nq, k), dtype=torch.int64, device=q.device),
+                            "D": torch.empty((nq, k), dtype=torch.float32, device=q.device),
+                            "I": torch.empty((nq, k), dtype=torch.int64, device=q.device),
+                            "pushed": None} for _ in range(S)]
+        slot, epoch = self._step % S, self._step // S + 1
+        self._step += 1
+        b = self._slots[slot]
+        cur = torch.cuda.current_stream(q.device)
+        if b["pushed"] is not None:                     # the push of search (step - S) has read this keys buffer
+            cur.wait_event(b["pushed"])
+        self.local.search_keys_tensor(q, k, id_offset=self.id_offset, out=b["keys"])
+        scored = torch.cuda.Event()
+        scored.record(cur)
+        comm = self._comm
+        comm.wait_event(scored)                          # also orders the merge behind every consumer of D / I[slot]
+        cs = comm.cuda_stream                            # that was queued on the current stream before this search
+        self._mail.push(b["keys"].data_ptr(), nq * k, slot, epoch, cs)
+        b["pushed"] = torch.cuda.Event()
+        b["pushed"].record(comm)
+        self._mail.wait(slot, epoch, cs)
+        from . import _native as nat
+        nat.check(nat.lib.ivr_topk_merge_keys_device(self.device, self._mail.slot_ptr(slot), self.world, nq, k,
+                                                     b["D"].data_ptr(), b["I"].data_ptr(), cs))
+        done = torch.cuda.Event()
+        done.record(comm)
+        return PendingSearch(b["D"], b["I"], done, comm)
+
+    def close(self) -> None:
+        """Collective: waits for every rank's outstanding exchanges, then frees the mailbox."""
+        if self._mail is not None:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._mail.close()
+            self._mail = None
 
 
 # ---------------------------------------------------------------------------

@@ -45,7 +45,7 @@ def _merge(keys_parts, k):
     return torch.from_numpy(D), torch.from_numpy(I)
 
 
-def _worker(rank, world, port, n, d, k, out):
+def _worker(rank, world, port, n, d, k, weights, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -53,10 +53,16 @@ def _worker(rank, world, port, n, d, k, out):
         xb = synth.clip_like(n, d, seed=21, n_centres=64)
         xq = synth.clip_like(9, d, seed=22, n_centres=64)
         sh = ShardedFlatIP(d, local_index=_OracleLocal(d), merge=_merge)
-        sh.add_global(xb)
-        off = partition_rows(n, world)
+        assert sh.exchange == "nccl"                     # injected back-ends use the collective transport
+        sh.add_global(xb, weights=weights)
+        off = partition_rows(n, world, weights)
         assert sh.id_offset == off[rank] and sh.local.ntotal == off[rank + 1] - off[rank]
         D, I = sh.search(torch.from_numpy(xq), k)
+        pend = [sh.search_async(torch.from_numpy(xq), k) for _ in range(3)]      # the async front end, same hits
+        for h in pend:
+            h.synchronize()
+            D2, I2 = h.result(copy=False)
+            assert np.array_equal(I2.numpy(), I.numpy()) and np.array_equal(D2.numpy(), D.numpy())
         full = flat_ip.IndexFlatIP(d)
         full.add(xb)
         Dr, Ir = full.search(xq, k)
@@ -66,15 +72,15 @@ def _worker(rank, world, port, n, d, k, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,k", [(1001, 10), (7, 10)])
-def test_sharded_search_world2(n, k):
+@pytest.mark.parametrize("n,k,weights", [(1001, 10, None), (7, 10, None), (1001, 10, [1.0, 3.0])])
+def test_sharded_search_world2(n, k, weights):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, n, 32, k, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n, 32, k, weights, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
 
 
@@ -84,6 +90,26 @@ def test_partition_rows():
     assert off[0] == 0 and off[-1] == 100_000_000 and np.all(np.diff(off) == 12_500_000)
     off = partition_rows(10, 4)
     assert off.tolist() == [0, 2, 5, 7, 10]
+
+
+def test_partition_rows_by_measured_speed():
+    """Shards sized by each GPU's scoring rate: shares proportional to the weights, boundaries aligned, every
+    row owned exactly once; equal weights reproduce the balanced partition."""
+    from ivr_b200.sharded import partition_rows
+    n = 100_000_000
+    rates = [305.1, 310.4, 308.0, 303.9, 309.2, 306.6, 307.7, 304.3]
+    off = partition_rows(n, 8, weights=rates, align=1024)
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) > 0)
+    assert np.all(off[1:-1] % 1024 == 0)
+    share = np.diff(off) / n
+    assert np.allclose(share, np.array(rates) / sum(rates), atol=2e-5)
+    t = np.diff(off) / np.array(rates)                       # predicted time per rank: flat within the alignment
+    assert t.max() / t.min() < 1.0002
+    assert partition_rows(n, 8, weights=[2.0] * 8).tolist() == partition_rows(n, 8).tolist()
+    assert partition_rows(5, 4, weights=[1, 1, 1, 1], align=1024).tolist()[-1] == 5    # tiny index: still covers all rows
+    for bad in ([1.0, 0.0], [1.0, float("nan")], [1.0]):
+        with pytest.raises(ValueError):
+            partition_rows(10, 2, weights=bad)
 
 
 # ---------------------------------------------------------------------------
