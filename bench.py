@@ -74,7 +74,9 @@ def parse_args():
     p.add_argument("--cpu-dedup-frames", type=int, default=10_000)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--equal-shards", action="store_true",
-                   help="N > 1: split the rows equally instead of by each GPU's measured scoring rate")
+                   help="N > 1: static equal shards (no replicated boundary rows, no elastic boundaries)")
+    p.add_argument("--shard-margin", type=float, default=0.04,
+                   help="N > 1: fraction of a shard every rank also stores from either neighbour (elastic boundaries)")
     p.add_argument("--no-extras", action="store_true",
                    help="skip the informational legs (BASELINE configs A, B, C, the production-shaped cell)")
     return p.parse_args()
@@ -541,50 +543,45 @@ def run_ours(args):
     local.search_path = args.path
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    def build_shard(row0, row1, check, headroom=1.0):
-        """Rows [row0, row1) of the synthetic matrix (generated chunk by chunk; a rank whose boundary falls inside a
-        chunk keeps its part of it) + when `check`: an exact fp32 top-k of the check queries over the SAME rows."""
-        local.reset()
-        local.reserve(int((row1 - row0) * headroom))
+    def build_shard(row0, row1, lo, hi):
+        """Stores rows [lo, hi) of the synthetic matrix (generated chunk by chunk; a rank whose boundary falls inside
+        a chunk keeps its part of it) and returns an exact fp32 top-k of the check queries over ITS OWN rows
+        [row0, row1) -- the checker the parity gate merges across ranks."""
+        local.reserve(hi - lo)
         bd = torch.full((n_chk, k), -float("inf"), device=dev)
         bi = torch.full((n_chk, k), -1, dtype=torch.int64, device=dev)
-        for c in range(row0 // chunk_rows, (row1 + chunk_rows - 1) // chunk_rows):
+        for c in range(lo // chunk_rows, (hi + chunk_rows - 1) // chunk_rows):
             x = gen_rows(c, chunk_rows, dim, cen, dev)
-            lo, hi = max(row0, c * chunk_rows), min(row1, (c + 1) * chunk_rows)
-            if hi - lo < chunk_rows:
-                x = x[lo - c * chunk_rows:hi - c * chunk_rows].contiguous()
+            c0 = c * chunk_rows
+            a, b = max(lo, c0), min(hi, c0 + chunk_rows)
+            xs = x if b - a == chunk_rows else x[a - c0:b - c0].contiguous()
             if index:
-                index.add_local(x, row0, n_total)
+                index.add_local(xs, lo, n_total)
             else:
-                local.add(x)
-            if check:
-                s = q_chk @ x.T
-                d_, i_ = torch.topk(s, min(k, x.shape[0]), dim=1)
-                cd, ci = torch.cat([bd, d_], 1), torch.cat([bi, i_ + lo], 1)
+                local.add(xs)
+            a, b = max(row0, c0), min(row1, c0 + chunk_rows)
+            if b > a:
+                s = q_chk @ x[a - c0:b - c0].T
+                d_, i_ = torch.topk(s, min(k, b - a), dim=1)
+                cd, ci = torch.cat([bd, d_], 1), torch.cat([bi, i_ + a], 1)
                 o = torch.argsort(cd, dim=1, descending=True, stable=True)[:, :k]
                 bd, bi = torch.gather(cd, 1, o), torch.gather(ci, 1, o)
                 del s
-            del x
+            del x, xs
         torch.cuda.synchronize()
         return bd, bi
 
     t_build = time.perf_counter()
-    off = partition_rows(n_total, world, align=1)
-    balance = None
-    if world > 1 and not args.equal_shards:
-        # GPUs under the same power cap differ by a few per cent, and with the pipelined exchange the job runs at the
-        # pace of the slowest rank's own work: size the shards by MEASURED scoring speed.  Equal shards first, every
-        # rank times its local search, the rates are all-gathered and the matrix is re-partitioned.
-        build_shard(int(off[rank]), int(off[rank + 1]), check=False, headroom=1.06)   # room for a faster GPU's share
-        rate = torch.tensor([index.scoring_rate(q_dev, k, reps=8, warm=4)], device=dev, dtype=torch.float64)
-        rates = [torch.empty_like(rate) for _ in range(world)]
-        dist.all_gather(rates, rate)
-        rates = [float(r.item()) for r in rates]
-        off = partition_rows(n_total, world, weights=rates, align=1024)
-        balance = {"rows_per_ms_equal_shards": [round(r, 1) for r in rates],
-                   "rows_per_rank": [int(off[r + 1] - off[r]) for r in range(world)]}
+    off = partition_rows(n_total, world)
     row0, row1 = int(off[rank]), int(off[rank + 1])
-    best_d, best_i = build_shard(row0, row1, check=True)
+    # Elastic shard boundaries (N > 1): every rank also stores `margin` rows of either neighbour, so a boundary can
+    # move between two searches without moving data; ShardedFlatIP's controller sizes the windows by the measured
+    # scoring times (GPUs under the same power cap differ by a few per cent and drift with temperature).
+    margin = 0 if (world == 1 or args.equal_shards) else int(args.shard_margin * (n_total // world)) // 1024 * 1024
+    lo, hi = max(0, row0 - margin), min(n_total, row1 + margin)
+    best_d, best_i = build_shard(row0, row1, lo, hi)
+    if margin:
+        index.enable_elastic(off, margin, period=8)
     t_build = time.perf_counter() - t_build
 
     def search_dev(q):
@@ -625,6 +622,8 @@ def run_ours(args):
     del best_d, best_i
 
     # ---- value: whole-job throughput, inputs resident in HBM ---------------------------
+    if margin:
+        run_steps(4 * 8 + 2)                                     # four controller periods: the boundaries settle
     run_steps(args.warmup)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -658,7 +657,8 @@ def run_ours(args):
         kall = [torch.empty_like(kt) for _ in range(world)]
         dist.all_gather(kall, kt)
         k_ranks = [float(v.item()) for v in kall]
-    n_local = row1 - row0
+    rows_now = [int(v) for v in np.diff(index._bounds)] if margin else None
+    n_local = rows_now[rank] if margin else row1 - row0            # rows this rank scored in the last searches
     path = launches["path"]
     peaks = {}
     try:
@@ -740,6 +740,13 @@ def run_ours(args):
         cpu, _ = cpu_arm(args, xb_s, xq_s, steps=1, warmup=0)
         del xb_s
 
+    balance = None
+    if margin:
+        log = index.balance_log
+        balance = {"elastic_margin_rows": margin, "controller_period_searches": 8, "controller_steps": len(log),
+                   "rows_per_rank_now": [int(v) for v in np.diff(index._bounds)],
+                   "scoring_ms_per_rank_at_last_step": [round(t, 3) for t in log[-1][1]] if log else None,
+                   "scoring_ms_per_rank_equal_shards": [round(t, 3) for t in log[0][1]] if log else None}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -752,6 +759,7 @@ def run_ours(args):
                            " + k-way merge; two searches in flight" if index.exchange == "peer" else
                            " + one all_gather of packed 64-bit keys + k-way merge"),
                        "exchange": index.exchange if index else None, "shard_balance": balance,
+                       "rows_stored_per_gpu": hi - lo,
                        "build_s": round(t_build, 2)},
                "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                        "d2h_bytes_per_step": nq * k * 12},

@@ -104,6 +104,13 @@ IVR_API int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t 
 IVR_API int ivr_index_search_keys_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
                                  uint64_t* keys_dev, int64_t id_offset, int path, void* stream);
 
+/* Search window: until cleared (count < 0) every search on this handle scores only the stored rows
+ * [first, first + count) -- ids are still "stored row + id_offset", k > count pads as usual, a window reaching beyond
+ * ntotal fails the search with IVR_EINVAL.  No data moves: this is how a row shard that also holds a replica of its
+ * neighbours' boundary rows takes over or gives up rows between two searches (elastic shard boundaries,
+ * ShardedFlatIP; no counterpart in the reference, whose shards are whole remote servers: system.py:1715-1757). */
+IVR_API int ivr_index_set_window(ivr_index* idx, int64_t first, int64_t count);
+
 /* Kernel timing of the LAST ivr_index_search_device call (CUDA events recorded on
  * the launching stream, only when enabled).  ms[0] = dominant scoring+select kernel,
  * ms[1] = top-k merge kernel(s), ms[2] = query preparation; launches[0..2] = launch

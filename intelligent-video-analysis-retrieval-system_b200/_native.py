@@ -48,6 +48,7 @@ PROTOTYPES = {
                                           C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ivr_index_search_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                                C.c_int64, C.c_int, C.c_void_p]),
+    "ivr_index_set_window": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "ivr_index_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ivr_index_last_timing": (C.c_int, [C.c_void_p, _c_f32p, _c_intp]),
     "ivr_index_last_path": (C.c_int, [C.c_void_p]),

@@ -315,6 +315,15 @@ int ivr_index_reset(ivr_index* idx) {
     return IVR_OK;
 }
 
+int ivr_index_set_window(ivr_index* idx, int64_t first, int64_t count) {
+    if (!idx) { set_error("set_window: NULL index"); return IVR_EINVAL; }
+    if (count < 0) { idx->win_first = 0; idx->win_count = -1; return IVR_OK; }
+    if (first < 0) { set_error("set_window: first row must be >= 0 (got %lld)", static_cast<long long>(first)); return IVR_EINVAL; }
+    idx->win_first = first;
+    idx->win_count = count;
+    return IVR_OK;
+}
+
 int64_t ivr_index_ntotal(const ivr_index* idx) { return idx ? idx->ntotal : -1; }
 int ivr_index_dim(const ivr_index* idx) { return idx ? idx->dim : -1; }
 int ivr_index_device(const ivr_index* idx) { return idx ? idx->device : -1; }
@@ -355,6 +364,21 @@ static int choose_path(const ivr_index* idx, int64_t nq, int k, int path) {
     return path;
 }
 
+// While alive, the search back-ends see only the rows of the handle's search window (ivr_index_set_window): the row
+// block starts at the window's first row and holds win_count rows; reported ids are shifted back by the caller.
+struct RowWindow {
+    ivr_index* idx;
+    __half*    rows;
+    int64_t    ntotal, capacity;
+    explicit RowWindow(ivr_index* i) : idx(i), rows(i->rows), ntotal(i->ntotal), capacity(i->capacity) {
+        if (idx->win_count < 0) return;
+        idx->rows = rows + idx->win_first * idx->dpad;
+        idx->ntotal = idx->win_count;
+        idx->capacity = capacity - idx->win_first;
+    }
+    ~RowWindow() { idx->rows = rows; idx->ntotal = ntotal; idx->capacity = capacity; }
+};
+
 // D_dev == nullptr selects the packed-key output: I_dev then receives uint64 keys [nq, k]
 // (order_preserving(score) << 32 | ~(row + id_offset), 0 = padding) instead of int64 ids.
 static int search_device_impl(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_dev,
@@ -362,6 +386,16 @@ static int search_device_impl(ivr_index* idx, const float* q_dev, int64_t nq, in
     if (k <= 0) { set_error("search: k must be positive (got %d)", k); return IVR_EINVAL; }
     if (k > IVR_MAX_K) { set_error("search: k=%d exceeds IVR_MAX_K=%d", k, IVR_MAX_K); return IVR_EUNSUPPORTED; }
     if (nq == 0) return IVR_OK;
+    if (idx->win_count >= 0) {
+        if (idx->win_first + idx->win_count > idx->ntotal) {
+            set_error("search: the window [%lld, +%lld) reaches beyond the %lld rows of the index",
+                      static_cast<long long>(idx->win_first), static_cast<long long>(idx->win_count),
+                      static_cast<long long>(idx->ntotal));
+            return IVR_EINVAL;
+        }
+        id_offset += idx->win_first;                 // ids stay "stored row + id_offset"
+    }
+    RowWindow window(idx);
     IVR_CUDA(cudaSetDevice(idx->device));
     if (idx->rows_ready_set) IVR_CUDA(cudaStreamWaitEvent(st, idx->rows_ready, 0));   // rows added on another stream
     idx->launches[0] = idx->launches[1] = idx->launches[2] = 0;

@@ -12,6 +12,10 @@ struct ivr_index {
     int64_t  capacity = 0;        // rows allocated
     __half* rows = nullptr;          // [capacity, dpad] row-major fp16, HBM
 
+    // search window (ivr_index_set_window): searches score rows [win_first, win_first + win_count) only;
+    // win_count < 0 = the whole index
+    int64_t  win_first = 0, win_count = -1;
+
     cudaStream_t stream = nullptr;   // handle-owned stream for the host-pointer entry points
 
     // scratch, grown on demand (device)

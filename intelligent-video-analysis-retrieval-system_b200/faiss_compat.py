@@ -80,6 +80,11 @@ class IndexFlatIP:
     def reset(self):
         nat.check(nat.lib.ivr_index_reset(self._handle()))
 
+    def set_window(self, first: int = 0, count: int = -1):
+        """Searches score only the stored rows [first, first + count) until cleared (``count < 0``); ids stay
+        "stored row + id_offset".  No data moves (``ivr_index_set_window``)."""
+        nat.check(nat.lib.ivr_index_set_window(self._handle(), int(first), int(count)))
+
     def reserve(self, n_rows: int):
         nat.check(nat.lib.ivr_index_reserve(self._handle(), int(n_rows)))
 

@@ -53,6 +53,69 @@ def partition_rows(n_total: int, world_size: int, weights=None, align: int = 1) 
 MAX_SHARDED_ROWS = (1 << 32) - 1          # the exchange key holds a 32-bit global row id
 
 
+def rebalance_bounds(bounds, times_ms, nominal, margin: int, gain: float = 0.7, align: int = 1024) -> np.ndarray:
+    """One step of the elastic-boundary controller (pure, deterministic: every rank computes the same answer from
+    the same all-gathered times).  ``bounds`` [world + 1]: the boundaries the timed searches ran with; ``times_ms``
+    [world]: every rank's mean local scoring time.  Rank r's rate is rows / time; its target share is proportional to
+    its rate; the shares move ``gain`` of the way there.  Inner boundaries are rounded to ``align`` rows and stay
+    within ``margin`` rows of the ``nominal`` partition -- the rows both neighbours hold."""
+    bounds = np.asarray(bounds, dtype=np.int64)
+    nominal = np.asarray(nominal, dtype=np.int64)
+    t = np.asarray(times_ms, dtype=np.float64)
+    n = np.diff(bounds).astype(np.float64)
+    if len(t) != len(n) or np.any(n <= 0) or not np.all(np.isfinite(t)) or np.any(t <= 0):
+        return bounds.copy()
+    rate = n / t
+    share = n + gain * (n.sum() * rate / rate.sum() - n)
+    inner = bounds[0] + np.cumsum(share)[:-1]
+    inner = np.rint(inner / align).astype(np.int64) * align
+    inner = np.clip(inner, nominal[1:-1] - margin, nominal[1:-1] + margin)
+    out = bounds.copy()
+    out[1:-1] = inner
+    return np.maximum.accumulate(out)
+
+
+class _EventTimer:
+    """Local scoring time of the last searches from CUDA events on the scoring stream (no host sync at record time)."""
+
+    def __init__(self, depth: int):
+        self.depth, self.ring = depth, {}
+
+    def start(self, i):
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ring[i] = [e, None]
+
+    def stop(self, i):
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ring[i][1] = e
+        self.ring.pop(i - self.depth, None)
+
+    def mean_ms(self, lo: int, hi: int) -> float:
+        """Mean over searches [lo, hi); blocks the host until search hi - 1 has been scored."""
+        self.ring[hi - 1][1].synchronize()
+        return sum(self.ring[i][0].elapsed_time(self.ring[i][1]) for i in range(lo, hi)) / (hi - lo)
+
+
+class _WallTimer(_EventTimer):
+    """The same for host back-ends (CPU tests): the local search is synchronous."""
+
+    def start(self, i):
+        import time
+        self.ring[i] = [time.perf_counter(), None]
+
+    def stop(self, i):
+        import time
+        self.ring[i][1] = time.perf_counter()
+        self.ring.pop(i - self.depth, None)
+
+    def mean_ms(self, lo: int, hi: int) -> float:
+        return 1e3 * sum(self.ring[i][1] - self.ring[i][0] for i in range(lo, hi)) / (hi - lo)
+
+
 def _cuda_merge(device: int):
     from . import _native as nat
 
@@ -186,20 +249,34 @@ class ShardedFlatIP:
         self._comm = None          # side stream: push -> wait -> merge of consecutive searches, in order
         self._step = 0
         self._slots = None         # per slot: keys, D, I, pushed-event
+        # elastic shard boundaries (enabled by add_global / add_local with margin > 0)
+        self._nominal = None       # [world + 1] partition the shards were built for
+        self._bounds = None        # [world + 1] boundaries the NEXT search runs with (identical on every rank)
+        self._margin = 0           # rows of each neighbour this rank also stores on either side
+        self._period, self._gain = 8, 0.7
+        self._nsearch = 0
+        self._timer = None
+        self._ctl, self._ctl_ready = None, False   # host-side (gloo) group the controller all-gathers the times on
+        self.balance_log = []      # (search number, times_ms, rows per rank) of every controller step
 
     # ---- build ---------------------------------------------------------
-    def add_global(self, x, weights=None) -> None:
+    def add_global(self, x, weights=None, margin: int = 0) -> None:
         """Every rank passes the same [n, d] matrix (or a view of it); each keeps its block (``weights``: see
-        ``partition_rows``; the same on every rank)."""
+        ``partition_rows``; the same on every rank).  ``margin`` > 0 also keeps that many rows of either neighbour and
+        turns on the elastic boundaries (``enable_elastic``)."""
         n = x.shape[0]
         off = partition_rows(n, self.world, weights)
         if self.ntotal_global != 0:
             raise RuntimeError("add_global supports one contiguous build; use add_local to append")
         if n > MAX_SHARDED_ROWS:
             raise ValueError(f"a sharded index holds at most 2^32 - 1 rows in total (got {n})")
-        self.id_offset = int(off[self.rank])
-        self.local.add(x[off[self.rank]:off[self.rank + 1]])
+        lo = max(0, int(off[self.rank]) - int(margin))
+        hi = min(n, int(off[self.rank + 1]) + int(margin))
+        self.id_offset = lo
+        self.local.add(x[lo:hi])
         self.ntotal_global = n
+        if margin > 0 and self.world > 1:
+            self.enable_elastic(off, margin)
 
     def add_local(self, x_local, id_offset: int, ntotal_global: int) -> None:
         """This rank's pre-partitioned block (e.g. generated on device), with its global offset."""
@@ -209,6 +286,62 @@ class ShardedFlatIP:
             self.id_offset = int(id_offset)
         self.local.add(x_local)
         self.ntotal_global = int(ntotal_global)
+
+    def enable_elastic(self, nominal, margin: int, period: int = 8, gain: float = 0.7, ctl_group=None,
+                       timer=None) -> None:
+        """ELASTIC SHARD BOUNDARIES.  GPUs under the same power cap differ by a few per cent and drift with
+        temperature; with the pipelined exchange the job runs at the pace of the slowest rank's own work.  Every rank
+        therefore also stores ``margin`` rows of either neighbour (HBM is plentiful: + 2 * margin rows), which lets
+        the boundary between two ranks move between two searches WITHOUT moving data: each search scores the rows
+        ``[bounds[r], bounds[r+1])`` through ``ivr_index_set_window``.  Every ``period`` searches the ranks
+        all-gather their mean local scoring times on a host-side group and apply ``rebalance_bounds`` -- the same
+        deterministic step on every rank, so every row is scored by exactly one rank in every search and the hits
+        stay exactly those of the static partition.
+
+        ``nominal`` [world + 1]: the partition (the same on every rank); this rank must hold the rows
+        ``[nominal[r] - margin, nominal[r+1] + margin)`` clipped to the index, starting at ``id_offset``.
+        ``ctl_group``: a gloo group for the controller (created on first use otherwise -- collective)."""
+        nominal = np.asarray(nominal, dtype=np.int64)
+        if nominal.shape != (self.world + 1,) or nominal[0] != 0 or nominal[-1] != self.ntotal_global:
+            raise ValueError("nominal: offsets [world + 1] from 0 to ntotal")
+        lo = max(0, int(nominal[self.rank]) - int(margin))
+        hi = min(self.ntotal_global, int(nominal[self.rank + 1]) + int(margin))
+        if self.id_offset != lo or self.local.ntotal != hi - lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) for margin {margin}: it holds "
+                             f"[{self.id_offset}, {self.id_offset + self.local.ntotal})")
+        self._nominal, self._bounds, self._margin = nominal, nominal.copy(), int(margin)
+        self._period, self._gain = max(4, int(period)), float(gain)
+        self._ctl, self._ctl_ready, self._nsearch = ctl_group, ctl_group is not None, 0
+        self._timer = timer
+        self.balance_log = []
+
+    def _elastic_begin(self, q) -> int:
+        """Controller step (every ``period`` searches) + the row window of this search.  Returns the search number."""
+        import torch
+        import torch.distributed as dist
+        i, P = self._nsearch, self._period
+        self._nsearch += 1
+        if self._timer is None:
+            self._timer = _EventTimer(2 * P) if getattr(q, "is_cuda", False) else _WallTimer(2 * P)
+        if i >= P and i % P == 0:
+            # the two latest searches may still be in flight: use the P - 2 before them (all run with these bounds)
+            mine = torch.tensor([self._timer.mean_ms(i - P, i - 2)], dtype=torch.float64)
+            if not self._ctl_ready:                      # the controller talks on a HOST-side group: a GPU collective
+                if dist.get_backend(self.group) != "gloo":   # would hold SMs the scoring kernels need while it waits
+                    ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
+                    self._ctl = dist.new_group(ranks=ranks, backend="gloo")
+                else:
+                    self._ctl = self.group
+                self._ctl_ready = True
+            times = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(times, mine, group=self._ctl)
+            times = [float(t.item()) for t in times]
+            self._bounds = rebalance_bounds(self._bounds, times, self._nominal, self._margin, self._gain)
+            self.balance_log.append((i, times, np.diff(self._bounds).tolist()))
+        first = int(self._bounds[self.rank]) - self.id_offset
+        self.local.set_window(first, int(self._bounds[self.rank + 1] - self._bounds[self.rank]))
+        self._timer.start(i)
+        return i
 
     @property
     def ntotal(self) -> int:
@@ -250,7 +383,10 @@ class ShardedFlatIP:
         if self._keys is None or self._keys.shape != (nq, k) or self._keys.device != q.device:
             self._keys = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             self._gathered = torch.empty((self.world, nq, k), dtype=torch.int64, device=q.device)
+        i = self._elastic_begin(q) if self._bounds is not None else -1
         self.local.search_keys_tensor(q, k, id_offset=self.id_offset, out=self._keys)
+        if i >= 0:
+            self._timer.stop(i)
         dist.all_gather_into_tensor(self._gathered.view(self.world * nq, k), self._keys, group=self.group)
         D, I = self._merge(self._gathered, k)
         return PendingSearch(D, I, None, None)
@@ -310,7 +446,10 @@ class ShardedFlatIP:
         cur = torch.cuda.current_stream(q.device)
         if b["pushed"] is not None:                     # the push of search (step - S) has read this keys buffer
             cur.wait_event(b["pushed"])
+        i = self._elastic_begin(q) if self._bounds is not None else -1
         self.local.search_keys_tensor(q, k, id_offset=self.id_offset, out=b["keys"])
+        if i >= 0:
+            self._timer.stop(i)
         scored = torch.cuda.Event()
         scored.record(cur)
         comm = self._comm

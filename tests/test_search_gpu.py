@@ -800,3 +800,44 @@ def test_small_kernel_dump_mode_clustered_rows_overflow_the_pool_and_stay_exact(
     check(idx, ref, q, 100, path=2)
     check(idx, ref, q, 1000, path=2)
     assert idx.last_timing()["kernel"] == "search_mma_small_kernel"
+
+
+@pytest.mark.parametrize("nq,path", [(1, 1), (3, 0), (16, 0), (100, 0), (300, 2)])
+def test_search_window_scores_only_its_rows_and_keeps_stored_row_ids(nq, path):
+    """ivr_index_set_window (elastic shard boundaries): a windowed search equals the oracle over that row range,
+    ids are stored rows + id_offset, and two adjacent windows merged equal the whole index -- on every kernel path."""
+    import torch
+    n, d, k = 30000, 128, 50
+    xb = synth.clip_like(n, d, seed=61, n_centres=64)
+    xq = synth.clip_like(nq, d, seed=62, n_centres=64)
+    idx, ref = build(xb)
+    idx.search_path = path
+    cut = 12345
+    parts = []
+    for first, count in ((0, cut), (cut, n - cut)):
+        sub = flat_ip.IndexFlatIP(d)
+        sub.add(xb[first:first + count])
+        idx.set_window(first, count)
+        D, I = idx.search(xq, k)
+        Dr, Ir = sub.search(xq, k)
+        bad = comparator.compare_topk(D, I - first, Dr, Ir, lambda ids: sub.scores_of(xq, ids), TOL)
+        assert not bad, "\n".join(bad[:5])
+        assert I.min() >= first and I.max() < first + count
+        Dt, It = idx.search_tensor(torch.from_numpy(xq).cuda(), k, id_offset=1000)
+        assert np.array_equal(It.cpu().numpy(), I + 1000)
+        parts.append((D, I))
+    Dm, Im = flat_ip.merge_shard_results([p[0] for p in parts], [p[1] for p in parts], k)
+    Dr, Ir = ref.search(xq, k)
+    bad = comparator.compare_topk(Dm, Im, Dr, Ir, lambda ids: ref.scores_of(xq, ids), TOL)
+    assert not bad, "\n".join(bad[:5])
+    idx.set_window(5, 7)                              # fewer rows than k: padded like a 7-row index
+    D, I = idx.search(xq, k)
+    assert np.all(I[:, 7:] == -1) and np.all((I[:, :7] >= 5) & (I[:, :7] < 12))
+    idx.set_window(0, 0)                              # empty window: all padding
+    D, I = idx.search(xq, k)
+    assert np.all(I == -1)
+    idx.set_window(n - 10, 11)                        # reaches beyond the index
+    with pytest.raises(Exception, match="window"):
+        idx.search(xq, k)
+    idx.set_window()                                  # cleared: the whole index again
+    check(idx, ref, xq, k, path=path)

@@ -16,6 +16,18 @@ from oracle import flat_ip, synth
 class _OracleLocal:
     def __init__(self, d):
         self.ix = flat_ip.IndexFlatIP(d)
+        self._full, self._first = None, 0
+
+    def set_window(self, first=0, count=-1):
+        """ivr_index_set_window on the stand-in: searches see the stored rows [first, first + count) only."""
+        if self._full is None:
+            self._full = self.ix
+        if count < 0:
+            self.ix, self._first = self._full, 0
+            return
+        assert 0 <= first and first + count <= self._full.ntotal
+        self.ix, self._first = flat_ip.IndexFlatIP(self._full.d), first
+        self.ix.add(self._full.xb[first:first + count])
 
     @property
     def ntotal(self):
@@ -25,11 +37,13 @@ class _OracleLocal:
         self.ix.add(np.asarray(x))
 
     def search_tensor(self, q, k, id_offset=0):
+        id_offset += self._first
         D, I = self.ix.search(q.numpy(), k)
         return torch.from_numpy(D), torch.from_numpy(np.where(I >= 0, I + id_offset, -1))
 
     def search_keys_tensor(self, q, k, id_offset=0, out=None):
         """The packed-key protocol of faiss_compat.IndexFlatIP.search_keys_tensor, restated on the CPU."""
+        id_offset += self._first
         D, I = self.ix.search(q.numpy(), k)
         keys = torch.from_numpy(flat_ip.pack_keys(D, np.where(I >= 0, I + id_offset, -1)).view(np.int64))
         if out is None:
@@ -82,6 +96,87 @@ def test_sharded_search_world2(n, k, weights):
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, n, 32, k, weights, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+class _ScriptedTimer:
+    """Scoring times for the controller: rank 0's GPU is 'slower' per row than rank 1's."""
+
+    def __init__(self, index, ms_per_row):
+        self.index, self.ms_per_row = index, ms_per_row
+
+    def start(self, i):
+        pass
+
+    def stop(self, i):
+        pass
+
+    def mean_ms(self, lo, hi):
+        b = self.index._bounds
+        return float(b[self.index.rank + 1] - b[self.index.rank]) * self.ms_per_row
+
+
+def _elastic_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ivr_b200.sharded import ShardedFlatIP, partition_rows
+        n, d, k, margin = 4001, 32, 10, 700
+        xb = synth.clip_like(n, d, seed=41, n_centres=64)
+        full = flat_ip.IndexFlatIP(d)
+        full.add(xb)
+        sh = ShardedFlatIP(d, local_index=_OracleLocal(d), merge=_merge)
+        sh.add_global(xb, margin=margin)
+        nominal = partition_rows(n, world)
+        assert sh.id_offset == max(0, nominal[rank] - margin)
+        assert sh.local.ntotal == min(n, nominal[rank + 1] + margin) - sh.id_offset
+        sh.enable_elastic(nominal, margin, period=4, gain=1.0,
+                          timer=_ScriptedTimer(sh, 0.003 if rank == 0 else 0.001))
+        ok = True
+        for s_ in range(14):
+            xq = synth.clip_like(5, d, seed=300 + s_, n_centres=64)
+            D, I = sh.search(torch.from_numpy(xq), k)
+            Dr, Ir = full.search(xq, k)
+            ok = ok and np.array_equal(I.numpy(), Ir) and np.allclose(D.numpy(), Dr, atol=1e-6)
+        out[rank] = (bool(ok), [list(map(int, rows)) for _, _, rows in sh.balance_log])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_elastic_boundaries_world2_move_rows_to_the_faster_rank_and_stay_exact():
+    """Rank 0 is 3x slower per row: the controller (every 4 searches) hands its rows to rank 1 until the margin
+    stops it; both ranks apply the same boundaries; every search still returns exactly the full-index hits."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_elastic_worker, args=(2, port, out), nprocs=2, join=True)
+    res = dict(out)
+    assert res[0][0] and res[1][0]
+    assert res[0][1] == res[1][1] and len(res[0][1]) == 3          # steps at searches 4, 8, 12, identical on both ranks
+    first, last = res[0][1][0], res[0][1][-1]
+    assert first[0] < 2000 < first[1] and sum(first) == 4001
+    assert last == [2000 - 700, 2001 + 700]                        # clipped at the margin: rows both ranks hold
+
+
+def test_rebalance_bounds_controller():
+    from ivr_b200.sharded import partition_rows, rebalance_bounds
+    nom = partition_rows(100_000_000, 8)
+    speed = np.array([1.0, 1.03, 1.02, 1.0, 1.01, 1.01, 1.0, 0.99])
+    b = nom.copy()
+    for _ in range(5):
+        t = np.diff(b) / speed / 3e5
+        b = rebalance_bounds(b, t, nom, margin=500_000)
+        assert b[0] == 0 and b[-1] == 100_000_000 and np.all(np.diff(b) > 0)
+        assert np.all(np.abs(b - nom) <= 500_000) and np.all(b[1:-1] % 1024 == 0)
+    t = np.diff(b) / speed / 3e5
+    assert t.max() / t.mean() < 1.001                              # from 1.0175 with equal shards
+    # degenerate inputs leave the boundaries alone
+    assert rebalance_bounds(nom, [1.0] * 7 + [0.0], nom, 1000).tolist() == nom.tolist()
+    assert rebalance_bounds(nom, [float("nan")] * 8, nom, 1000).tolist() == nom.tolist()
+    # margin 0 = static partition
+    assert rebalance_bounds(nom, 1.0 / speed, nom, 0).tolist() == nom.tolist()
 
 
 def test_partition_rows():
