@@ -15,7 +15,12 @@
 namespace ivr {
 
 constexpr int kMergeThreads = 256;
-constexpr int kMergeFanIn   = 64;     // lists folded by one CTA in a non-final level
+// Lists folded by one CTA in a non-final level.  Up to k = 128 the candidates of 256 lists normally fit the
+// shared-memory staging buffer (kStageCap), so one CTA folds 256 lists (the 148 lists per query of the
+// row-tile-resident kernel: one level instead of two); larger k keeps the narrow fan-in of the in-place select.
+static int merge_fan_in(int k) { return k <= 128 ? 256 : 64; }
+constexpr int kStageCap   = 4096;     // keys of one (query, list group) staged in shared memory (32 KB)
+constexpr int kStageLists = 256;      // most lists per CTA on the staged path (= kMergeThreads: one count per thread)
 
 static int kpad_for(int k) { int p = 2; while (p < k) p <<= 1; return p; }
 
@@ -75,7 +80,63 @@ struct MergeShared {
     int      hist[256];
     uint64_t prefix, mask;
     int      remaining, done, n, neq, total;
+    int      off[kStageLists + 1];      // staged path: exclusive prefix sum of the list lengths
+    int      wsum[kMergeThreads / 32];
+    int      zeros;
 };
+
+// Staged path of block_select_sort.  The in-place select below walks the lists once per radix pass, one list per
+// warp step, and every step is a dependent pair of global loads (length, then entries): ~20 steps x 2 round trips x
+// up to 10 passes per CTA -- 150-500 us for a 4096-query merge, 1.3-2.2 ms per search, a fixed cost that weighed
+// 3-5 % on a 12.5 M-row shard (profiles/r2_launches_bench_n1.csv).  Here the lengths are fetched with ONE load per
+// thread, prefix-summed in shared memory, and the entries are fetched through a flattened index (every load of the
+// CTA independent, two round trips in total) into shared memory, where one bitonic sort yields the k best in order.
+// Returns -1 when the group does not qualify (dense input, > kStageLists lists, > kStageCap candidates).
+__device__ int block_stage_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
+                                MergeShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_l = l1 - l0;
+    if (in.dense || n_l > kStageLists || blockDim.x != kMergeThreads) return -1;
+    // 1. list lengths -> exclusive prefix sum (one length per thread)
+    int c = 0;
+    if (tid < n_l) c = in.counts ? in.counts[(l0 + tid) * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sh.wsum[warp] = incl;
+    if (tid == 0) sh.zeros = 0;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += sh.wsum[w];
+    sh.off[tid] = before + incl - c;
+    int total = 0;
+    for (int w = 0; w < kMergeThreads / 32; ++w) total += sh.wsum[w];
+    if (tid == 0) sh.off[kStageLists] = total;
+    if (total > kStageCap) { __syncthreads(); return -1; }      // uniform: every thread computed the same total
+    int np2 = kpad;
+    while (np2 < total) np2 <<= 1;
+    for (int i = total + tid; i < np2; i += kMergeThreads) s_keys[i] = 0ull;
+    __syncthreads();
+    // 2. flattened fetch: candidate idx lives in the list l with off[l] <= idx < off[l + 1]
+    const int es = in.interleave ? 32 : 1;
+    int zeros = 0;
+    for (int idx = tid; idx < total; idx += kMergeThreads) {
+        int lo = 0, hi = n_l;                                    // off[] is non-decreasing; empty lists are skipped
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.off[mid] <= idx) lo = mid; else hi = mid; }
+        const int l = l0 + lo;
+        const uint64_t* base = in.entries + l * in.list_stride +
+                               (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+        uint64_t key = base[static_cast<int64_t>(idx - sh.off[lo]) * es];
+        if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+        zeros += key == 0ull;
+        s_keys[idx] = key;
+    }
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if (lane == 0 && zeros) atomicAdd(&sh.zeros, zeros);
+    __syncthreads();
+    // 3. sort everything: the k best are the first k (padding keys are 0 = lowest)
+    block_bitonic_desc(s_keys, np2);
+    return min(total - sh.zeros, k);
+}
 
 // Block-level exact selection: the (at most) k largest keys of lists [l0, l1) of query q, sorted descending in
 // s_keys[0 .. kpad) (0-padded).  Returns the number of valid entries.  MSB-first 8-bit radix select on the 64-bit
@@ -83,6 +144,10 @@ struct MergeShared {
 __device__ int block_select_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
                                  MergeShared& sh) {
     const int tid = threadIdx.x;
+    {
+        const int staged = block_stage_sort(in, q, l0, l1, k, kpad, s_keys, sh);
+        if (staged >= 0) return staged;
+    }
     if (tid == 0) { sh.total = 0; sh.n = 0; sh.neq = 0; sh.prefix = 0; sh.mask = 0; sh.remaining = k; sh.done = 0; }
     for (int i = tid; i < kpad; i += blockDim.x) s_keys[i] = 0ull;
     __syncthreads();
@@ -356,10 +421,11 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
 
 
 size_t merge_tmp_entries(int n_lists, int64_t nq, int k) {
-    // levels shrink by kMergeFanIn; two ping-pong buffers sized for the first level
-    if (n_lists <= kMergeFanIn) return 0;
-    const int64_t g1 = (n_lists + kMergeFanIn - 1) / kMergeFanIn;
-    const int64_t g2 = (g1 + kMergeFanIn - 1) / kMergeFanIn;
+    // levels shrink by the fan-in; two ping-pong buffers sized for the first level
+    const int fan = merge_fan_in(k);
+    if (n_lists <= fan) return 0;
+    const int64_t g1 = (n_lists + fan - 1) / fan;
+    const int64_t g2 = (g1 + fan - 1) / fan;
     return static_cast<size_t>((g1 + g2) * nq * k);
 }
 
@@ -368,7 +434,8 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
                       cudaStream_t st, int* n_launches, const float* q_scale) {
     if (nq <= 0) return IVR_OK;
     const int kpad = kpad_for(k);
-    const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
+    const size_t smem = static_cast<size_t>(std::max(kpad, kStageCap)) * sizeof(uint64_t);
+    const int kMergeFanIn = merge_fan_in(k);
     MergeIn in = in0;
     int level = 0;
     uint64_t* ebuf = tmp_entries;
@@ -431,7 +498,8 @@ int merge_lists_keys(const MergeIn& in0, int64_t nq, int k, uint64_t* out_keys, 
                      uint64_t* tmp_entries, int* tmp_counts, cudaStream_t st, int* n_launches) {
     if (nq <= 0) return IVR_OK;
     const int kpad = kpad_for(k);
-    const size_t smem = static_cast<size_t>(kpad) * sizeof(uint64_t);
+    const size_t smem = static_cast<size_t>(std::max(kpad, kStageCap)) * sizeof(uint64_t);
+    const int kMergeFanIn = merge_fan_in(k);
     MergeIn in = in0;
     uint64_t* ebuf = tmp_entries;
     int*      cbuf = tmp_counts;
