@@ -525,7 +525,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")        # one node: the controller's host-side group needs no
+        dist.init_process_group("nccl", device_id=dev)           # resolvable hostname
 
     dim, k, nq, n_total = args.dim, args.k, args.nq, args.rows
     if n_total % GEN_CHUNK and n_total > GEN_CHUNK:
@@ -618,7 +619,8 @@ def run_ours(args):
         cd, ci = torch.cat(gd, 1), torch.cat(gi, 1)
         o = torch.argsort(cd, dim=1, descending=True, stable=True)[:, :k]
         best_d, best_i = torch.gather(cd, 1, o), torch.gather(ci, 1, o)
-    parity = parity_report(D[:n_chk].cpu().numpy(), I[:n_chk].cpu().numpy(), best_d.cpu().numpy(), best_i.cpu().numpy(), k)
+    exact_d, exact_i = best_d.cpu().numpy(), best_i.cpu().numpy()
+    parity = parity_report(D[:n_chk].cpu().numpy(), I[:n_chk].cpu().numpy(), exact_d, exact_i, k)
     del best_d, best_i
 
     # ---- value: whole-job throughput, inputs resident in HBM ---------------------------
@@ -742,6 +744,12 @@ def run_ours(args):
 
     balance = None
     if margin:
+        # the same gate once more, with the shard boundaries where the controller has moved them (pipelined front end)
+        D, I = index.search_async(q_dev, k).result(copy=True)
+        torch.cuda.synchronize()
+        again = parity_report(D[:n_chk].cpu().numpy(), I[:n_chk].cpu().numpy(), exact_d, exact_i, k)
+        parity["after_the_boundaries_moved"] = {key: again[key] for key in
+                                                ("status", "max_abs_score_error_vs_exact_fp32", "tie_band_substitutions")}
         log = index.balance_log
         balance = {"elastic_margin_rows": margin, "controller_period_searches": 8, "controller_steps": len(log),
                    "rows_per_rank_now": [int(v) for v in np.diff(index._bounds)],

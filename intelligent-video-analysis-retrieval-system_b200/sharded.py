@@ -327,17 +327,27 @@ class ShardedFlatIP:
             # the two latest searches may still be in flight: use the P - 2 before them (all run with these bounds)
             mine = torch.tensor([self._timer.mean_ms(i - P, i - 2)], dtype=torch.float64)
             if not self._ctl_ready:                      # the controller talks on a HOST-side group: a GPU collective
-                if dist.get_backend(self.group) != "gloo":   # would hold SMs the scoring kernels need while it waits
-                    ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
-                    self._ctl = dist.new_group(ranks=ranks, backend="gloo")
-                else:
-                    self._ctl = self.group
+                try:                                     # would hold SMs the scoring kernels need while it waits
+                    if dist.get_backend(self.group) != "gloo":
+                        ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
+                        self._ctl = dist.new_group(ranks=ranks, backend="gloo")
+                    else:
+                        self._ctl = self.group
+                except Exception as e:                   # no host-side transport on this box (every rank alike):
+                    import warnings                      # keep the boundaries where they are
+                    warnings.warn(f"elastic shard boundaries disabled: cannot create the gloo control group ({e})")
+                    self._period = 1 << 62
+                    self._ctl_ready = True
+                    return self._elastic_window(i)
                 self._ctl_ready = True
             times = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(times, mine, group=self._ctl)
             times = [float(t.item()) for t in times]
             self._bounds = rebalance_bounds(self._bounds, times, self._nominal, self._margin, self._gain)
             self.balance_log.append((i, times, np.diff(self._bounds).tolist()))
+        return self._elastic_window(i)
+
+    def _elastic_window(self, i: int) -> int:
         first = int(self._bounds[self.rank]) - self.id_offset
         self.local.set_window(first, int(self._bounds[self.rank + 1] - self._bounds[self.rank]))
         self._timer.start(i)
