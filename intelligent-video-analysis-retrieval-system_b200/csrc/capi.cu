@@ -539,7 +539,7 @@ int ivr_topk_merge_keys_device(int device, const uint64_t* keys_parts, int n_par
     }
     if (k > IVR_MAX_K) { set_error("topk_merge_keys: k=%d exceeds IVR_MAX_K", k); return IVR_EUNSUPPORTED; }
     if (merge_tmp_entries(n_parts, nq, k) != 0) {     // one merge level needs no scratch: no allocation on this path
-        set_error("topk_merge_keys: %d parts need more than one merge level (at most 256 parts up to k = 128, 64 beyond)", n_parts);
+        set_error("topk_merge_keys: at most 64 parts (got %d)", n_parts);
         return IVR_EUNSUPPORTED;
     }
     if (nq == 0) return IVR_OK;

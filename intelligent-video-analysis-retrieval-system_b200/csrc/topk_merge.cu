@@ -11,16 +11,22 @@
 #include "index.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace ivr {
 
 constexpr int kMergeThreads = 256;
-// Lists folded by one CTA in a non-final level.  Up to k = 128 the candidates of 256 lists normally fit the
-// shared-memory staging buffer (kStageCap), so one CTA folds 256 lists (the 148 lists per query of the
-// row-tile-resident kernel: one level instead of two); larger k keeps the narrow fan-in of the in-place select.
-static int merge_fan_in(int k) { return k <= 128 ? 256 : 64; }
-constexpr int kStageCap   = 4096;     // keys of one (query, list group) staged in shared memory (32 KB)
-constexpr int kStageLists = 256;      // most lists per CTA on the staged path (= kMergeThreads: one count per thread)
+// Lists folded by one CTA in a non-final level.  A CTA that holds the list lengths in shared memory (<= kFlatLists
+// lists) fetches every candidate through a flattened index, so a wide fan-in costs no dependent-load chain: the 148
+// lists per query of the row-tile-resident kernel fold in ONE level -- wherever the batch alone keeps the machine full
+// of CTAs.  Few queries x many lists (the small-batch kernel: 592 lists for <= 128 queries) keep the narrow fan-in: they
+// need the CTAs of the first level.
+static int merge_fan_in(int k, int64_t nq, int n_lists) {
+    const int64_t ctas_wide = nq * ((n_lists + 255) / 256);
+    return (k <= 128 && ctas_wide >= 1024) ? 256 : 64;
+}
+constexpr int kStageCap  = 2048;      // keys of one (query, list group) staged in shared memory (16 KB)
+constexpr int kFlatLists = 256;       // most lists per CTA on the flattened path (= kMergeThreads: one length per thread)
 
 static int kpad_for(int k) { int p = 2; while (p < k) p <<= 1; return p; }
 
@@ -80,74 +86,178 @@ struct MergeShared {
     int      hist[256];
     uint64_t prefix, mask;
     int      remaining, done, n, neq, total;
-    int      off[kStageLists + 1];      // staged path: exclusive prefix sum of the list lengths
+    int      off[kFlatLists + 1];       // flattened path: exclusive prefix sum of the list lengths
     int      wsum[kMergeThreads / 32];
-    int      zeros;
 };
 
-// Staged path of block_select_sort.  The in-place select below walks the lists once per radix pass, one list per
-// warp step, and every step is a dependent pair of global loads (length, then entries): ~20 steps x 2 round trips x
-// up to 10 passes per CTA -- 150-500 us for a 4096-query merge, 1.3-2.2 ms per search, a fixed cost that weighed
-// 3-5 % on a 12.5 M-row shard (profiles/r2_launches_bench_n1.csv).  Here the lengths are fetched with ONE load per
-// thread, prefix-summed in shared memory, and the entries are fetched through a flattened index (every load of the
-// CTA independent, two round trips in total) into shared memory, where one bitonic sort yields the k best in order.
-// Returns -1 when the group does not qualify (dense input, > kStageLists lists, > kStageCap candidates).
-__device__ int block_stage_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
-                                MergeShared& sh) {
+// k-th-largest search, one 8-bit digit: warp 0 scans the 256-bin histogram from the top bin down (32 bins per step,
+// shuffle prefix sums) and publishes the digit, the rank that remains inside its bin and whether the whole bin is
+// needed (then the select is finished).  Call with the histogram complete (after a barrier); ends with a barrier.
+__device__ __forceinline__ void radix_scan_bins(MergeShared& sh, uint64_t prefix, uint64_t mask, int remaining, int shift) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        int cum_before = 0, found = 0, rem_after = remaining;
+        bool hit_any = false;
+        for (int base = 224; base >= 0 && !hit_any; base -= 32) {
+            const int c = sh.hist[base + 31 - lane];                 // lane 0 holds the highest bin of the group
+            int incl = c;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const unsigned hit = __ballot_sync(0xffffffffu, cum_before + incl >= remaining);
+            if (hit) {
+                const int l0 = __ffs(hit) - 1;
+                found = base + 31 - l0;
+                rem_after = remaining - (cum_before + __shfl_sync(0xffffffffu, incl - c, l0));
+                hit_any = true;
+            }
+            cum_before += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {                                             // fewer than `remaining` keys match: bin 0 takes the rest
+            if (!hit_any) { found = 0; rem_after = remaining - (cum_before - sh.hist[0]); }
+            sh.remaining = rem_after;
+            sh.prefix = prefix | (static_cast<uint64_t>(found) << shift);
+            sh.mask = mask | (0xffull << shift);
+            sh.done = (sh.hist[found] == rem_after);                 // the whole bin is needed: stop early
+        }
+    }
+    __syncthreads();
+}
+
+// The k best keys are in s_keys[0 .. kpad) in any order (0-padded): sort them descending.  Up to 256 slots one warp
+// sorts them in registers (no block barrier per network stage); larger k uses the block-wide network.
+__device__ __forceinline__ void sort_result(uint64_t* s_keys, int kpad) {
+    __syncthreads();
+    if (kpad > 256) { block_bitonic_desc(s_keys, kpad); return; }
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        auto run = [&](auto tag) {
+            constexpr int E = decltype(tag)::value;
+            uint64_t v[E];
+#pragma unroll
+            for (int j = 0; j < E; ++j) { const int g = lane * E + j; v[j] = g < kpad ? s_keys[g] : 0ull; }
+            warp_sort_desc<E>(v, lane);
+#pragma unroll
+            for (int j = 0; j < E; ++j) { const int g = lane * E + j; if (g < kpad) s_keys[g] = v[j]; }
+        };
+        if (kpad <= 32) run(std::integral_constant<int, 1>{});
+        else if (kpad <= 64) run(std::integral_constant<int, 2>{});
+        else if (kpad <= 128) run(std::integral_constant<int, 4>{});
+        else run(std::integral_constant<int, 8>{});
+    }
+    __syncthreads();
+}
+
+// Flattened path of block_select_sort (<= kFlatLists lists, not dense).  The in-place select further down walks the
+// lists once per radix pass, one list per warp step, every step a dependent pair of global loads (length, then
+// entries): ~20 steps x 2 round trips x up to 10 passes per CTA.  Here the lengths are fetched with ONE load per thread
+// and prefix-summed in shared memory; candidate idx of the group is then addressed directly (binary search of its list
+// in the prefix sums), so all loads of a pass are independent.  Up to kStageCap candidates are fetched once into shared
+// memory (STAGED) and every radix pass runs there; larger groups re-read global memory through the same flattened index.
+// The k-th largest key is found digit by digit (8 bits, shared histogram, warp-parallel bin scan), the survivors are
+// compacted into s_keys[0 .. kpad) and sorted by one warp.
+template <bool STAGED>
+__device__ __forceinline__ uint64_t flat_key(const MergeIn& in, int64_t q, int l0, int n_l, int idx,
+                                             const uint64_t* stage, const MergeShared& sh) {
+    if (STAGED) return stage[idx];
+    int lo = 0, hi = n_l;                                // off[] is non-decreasing: the last list with off <= idx is
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.off[mid] <= idx) lo = mid; else hi = mid; }   // non-empty
+    const uint64_t* base = in.entries + (l0 + lo) * in.list_stride +
+                           (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
+    uint64_t key = base[static_cast<int64_t>(idx - sh.off[lo]) * (in.interleave ? 32 : 1)];
+    if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
+    return key;
+}
+
+template <bool STAGED>
+__device__ int flat_select(const MergeIn& in, int64_t q, int l0, int n_l, int total, int k, int kpad, uint64_t* s_keys,
+                           const uint64_t* stage, MergeShared& sh) {
+    const int tid = threadIdx.x;
+    uint64_t prefix = 0, mask = 0;
+    int remaining = k;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        sh.hist[tid] = 0;                                // kMergeThreads == 256 bins
+        __syncthreads();
+        for (int idx = tid; idx < total; idx += kMergeThreads) {
+            const uint64_t key = flat_key<STAGED>(in, q, l0, n_l, idx, stage, sh);
+            if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & 0xff], 1);
+        }
+        __syncthreads();
+        radix_scan_bins(sh, prefix, mask, remaining, shift);
+        prefix = sh.prefix; mask = sh.mask; remaining = sh.remaining;
+        if (sh.done) break;
+    }
+    // keys above the k-th digit string are in; of the keys equal to it, `remaining` (all of them when the bin was
+    // needed whole; any `remaining` of them otherwise -- they can differ only below the bits examined, i.e. not at all
+    // after 8 passes)
+    int zeros = 0;
+    for (int idx = tid; idx < total; idx += kMergeThreads) {
+        const uint64_t key = flat_key<STAGED>(in, q, l0, n_l, idx, stage, sh);
+        zeros += key == 0ull;
+        const uint64_t km = key & mask;
+        if (km > prefix) {
+            s_keys[atomicAdd(&sh.n, 1)] = key;
+        } else if (km == prefix) {
+            const int e = atomicAdd(&sh.neq, 1);
+            if (e < remaining) s_keys[k - remaining + e] = key;      // tail slots, disjoint from the > slots
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if ((tid & 31) == 0 && zeros) atomicAdd(&sh.total, zeros);       // sh.total counts the padding keys here
+    sort_result(s_keys, kpad);
+    return min(total - sh.total, k);
+}
+
+// Returns -1 when the group does not qualify (dense input, > kFlatLists lists).  s_keys holds kpad + kStageCap keys.
+__device__ int block_flat_select_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
+                                      MergeShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = l1 - l0;
-    if (in.dense || n_l > kStageLists || blockDim.x != kMergeThreads) return -1;
-    // 1. list lengths -> exclusive prefix sum (one length per thread)
+    if (in.dense || n_l > kFlatLists || blockDim.x != kMergeThreads) return -1;
+    // list lengths -> exclusive prefix sum (one length per thread)
     int c = 0;
     if (tid < n_l) c = in.counts ? in.counts[(l0 + tid) * in.cnt_list_stride + q * in.cnt_q_stride] : in.fixed_count;
     int incl = c;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) sh.wsum[warp] = incl;
-    if (tid == 0) sh.zeros = 0;
+    if (tid == 0) { sh.total = 0; sh.n = 0; sh.neq = 0; }
+    for (int i = tid; i < kpad; i += kMergeThreads) s_keys[i] = 0ull;
     __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += sh.wsum[w];
+    int before = 0, total = 0;
+    for (int w = 0; w < kMergeThreads / 32; ++w) { const int v = sh.wsum[w]; if (w < warp) before += v; total += v; }
     sh.off[tid] = before + incl - c;
-    int total = 0;
-    for (int w = 0; w < kMergeThreads / 32; ++w) total += sh.wsum[w];
-    if (tid == 0) sh.off[kStageLists] = total;
-    if (total > kStageCap) { __syncthreads(); return -1; }      // uniform: every thread computed the same total
-    int np2 = kpad;
-    while (np2 < total) np2 <<= 1;
-    for (int i = total + tid; i < np2; i += kMergeThreads) s_keys[i] = 0ull;
+    uint64_t* stage = s_keys + kpad;
     __syncthreads();
-    // 2. flattened fetch: candidate idx lives in the list l with off[l] <= idx < off[l + 1]
-    const int es = in.interleave ? 32 : 1;
-    int zeros = 0;
-    for (int idx = tid; idx < total; idx += kMergeThreads) {
-        int lo = 0, hi = n_l;                                    // off[] is non-decreasing; empty lists are skipped
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.off[mid] <= idx) lo = mid; else hi = mid; }
-        const int l = l0 + lo;
-        const uint64_t* base = in.entries + l * in.list_stride +
-                               (in.interleave ? (q >> 5) * in.q_stride * 32 + (q & 31) : q * in.q_stride);
-        uint64_t key = base[static_cast<int64_t>(idx - sh.off[lo]) * es];
-        if (in.raw) key = make_key(__uint_as_float(static_cast<uint32_t>(key)), static_cast<uint32_t>(key >> 32));
-        zeros += key == 0ull;
-        s_keys[idx] = key;
+    if (total <= kpad) {                                 // everything survives: fetch straight into the result slots
+        int zeros = 0;
+        for (int idx = tid; idx < total; idx += kMergeThreads) {
+            const uint64_t key = flat_key<false>(in, q, l0, n_l, idx, stage, sh);
+            zeros += key == 0ull;
+            s_keys[idx] = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+        if (lane == 0 && zeros) atomicAdd(&sh.total, zeros);
+        sort_result(s_keys, kpad);
+        return min(total - sh.total, k);
     }
-    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
-    if (lane == 0 && zeros) atomicAdd(&sh.zeros, zeros);
-    __syncthreads();
-    // 3. sort everything: the k best are the first k (padding keys are 0 = lowest)
-    block_bitonic_desc(s_keys, np2);
-    return min(total - sh.zeros, k);
+    if (total <= kStageCap) {
+        for (int idx = tid; idx < total; idx += kMergeThreads) stage[idx] = flat_key<false>(in, q, l0, n_l, idx, stage, sh);
+        __syncthreads();
+        return flat_select<true>(in, q, l0, n_l, total, k, kpad, s_keys, stage, sh);
+    }
+    return flat_select<false>(in, q, l0, n_l, total, k, kpad, s_keys, stage, sh);
 }
 
 // Block-level exact selection: the (at most) k largest keys of lists [l0, l1) of query q, sorted descending in
 // s_keys[0 .. kpad) (0-padded).  Returns the number of valid entries.  MSB-first 8-bit radix select on the 64-bit
-// keys, then a shared-memory bitonic sort.  Every thread of the block must call it.
+// keys, then a sort of the survivors.  Every thread of the block must call it.
 __device__ int block_select_sort(const MergeIn& in, int64_t q, int l0, int l1, int k, int kpad, uint64_t* s_keys,
                                  MergeShared& sh) {
     const int tid = threadIdx.x;
     {
-        const int staged = block_stage_sort(in, q, l0, l1, k, kpad, s_keys, sh);
-        if (staged >= 0) return staged;
+        const int flat = block_flat_select_sort(in, q, l0, l1, k, kpad, s_keys, sh);
+        if (flat >= 0) return flat;
     }
+    // in-place select: dense input (materialised scores) or more than kFlatLists lists
     if (tid == 0) { sh.total = 0; sh.n = 0; sh.neq = 0; sh.prefix = 0; sh.mask = 0; sh.remaining = k; sh.done = 0; }
     for (int i = tid; i < kpad; i += blockDim.x) s_keys[i] = 0ull;
     __syncthreads();
@@ -174,19 +284,7 @@ __device__ int block_select_sort(const MergeIn& in, int64_t q, int l0, int l1, i
                 if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & 0xff], 1);
             });
             __syncthreads();
-            if (tid == 0) {
-                int cum = 0, b = 255;
-                for (; b > 0; --b) {
-                    const int c = sh.hist[b];
-                    if (cum + c >= remaining) break;
-                    cum += c;
-                }
-                sh.remaining = remaining - cum;
-                sh.prefix = prefix | (static_cast<uint64_t>(b) << shift);
-                sh.mask = mask | (0xffull << shift);
-                sh.done = (sh.hist[b] == remaining - cum);   // the whole bin is needed: stop early
-            }
-            __syncthreads();
+            radix_scan_bins(sh, prefix, mask, remaining, shift);
             prefix = sh.prefix; mask = sh.mask; remaining = sh.remaining;
             if (sh.done) break;
         }
@@ -200,8 +298,7 @@ __device__ int block_select_sort(const MergeIn& in, int64_t q, int l0, int l1, i
             }
         });
     }
-    __syncthreads();
-    block_bitonic_desc(s_keys, kpad);
+    sort_result(s_keys, kpad);
     return min(total, k);
 }
 
@@ -422,7 +519,7 @@ merge_select_kernel(MergeIn in, MergeOut out, SelectArgs sa, int k, int kpad) {
 
 size_t merge_tmp_entries(int n_lists, int64_t nq, int k) {
     // levels shrink by the fan-in; two ping-pong buffers sized for the first level
-    const int fan = merge_fan_in(k);
+    const int fan = merge_fan_in(k, nq, n_lists);
     if (n_lists <= fan) return 0;
     const int64_t g1 = (n_lists + fan - 1) / fan;
     const int64_t g2 = (g1 + fan - 1) / fan;
@@ -434,8 +531,8 @@ int merge_lists_final(const MergeIn& in0, int64_t nq, int k, float* D_dev, int64
                       cudaStream_t st, int* n_launches, const float* q_scale) {
     if (nq <= 0) return IVR_OK;
     const int kpad = kpad_for(k);
-    const size_t smem = static_cast<size_t>(std::max(kpad, kStageCap)) * sizeof(uint64_t);
-    const int kMergeFanIn = merge_fan_in(k);
+    const size_t smem = static_cast<size_t>(kpad + kStageCap) * sizeof(uint64_t);
+    const int kMergeFanIn = merge_fan_in(k, nq, in0.n_lists);
     MergeIn in = in0;
     int level = 0;
     uint64_t* ebuf = tmp_entries;
@@ -498,8 +595,8 @@ int merge_lists_keys(const MergeIn& in0, int64_t nq, int k, uint64_t* out_keys, 
                      uint64_t* tmp_entries, int* tmp_counts, cudaStream_t st, int* n_launches) {
     if (nq <= 0) return IVR_OK;
     const int kpad = kpad_for(k);
-    const size_t smem = static_cast<size_t>(std::max(kpad, kStageCap)) * sizeof(uint64_t);
-    const int kMergeFanIn = merge_fan_in(k);
+    const size_t smem = static_cast<size_t>(kpad + kStageCap) * sizeof(uint64_t);
+    const int kMergeFanIn = merge_fan_in(k, nq, in0.n_lists);
     MergeIn in = in0;
     uint64_t* ebuf = tmp_entries;
     int*      cbuf = tmp_counts;
