@@ -35,6 +35,8 @@
 // Algorithmic work: 2 * ntotal * dpad * nq FLOP per search.
 #include "mma_common.cuh"
 
+#include <cmath>
+
 // Pipeline probes (epilogue skipped / tcgen05.ld only) return garbage results: they exist only in builds made
 // with -DIVR_PROBES (tools/probe_epilogue.sh) and are compiled out of the shipped library.
 #ifdef IVR_PROBES
@@ -862,12 +864,15 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
     const int64_t nq_pad = static_cast<int64_t>(tq) * mq;
     const int tile_rows = xres ? xres_tile_rows(idx) : kTileN;     // both phases use the same tile size
     const int64_t nt = (idx->ntotal + tile_rows - 1) / tile_rows;
-    // Launch boundaries (in row tiles).  The first launch covers a small prefix (IVR_MMA_PHASE0_ROWS, 8 k rows:
-    // measured against 2 k .. 32 k on 100 k .. 100 M rows -- config A 0.65 -> 0.50 ms, 1 M x 4096 queries 5.0 -> 4.2 ms,
-    // neutral from 10 M rows up; profiles/r2_phase0_rows.txt), every further one IVR_MMA_PHASE_RATIO (16) times the
-    // rows seen so far, the last one the rest:
-    // a launch admits ~k * ratio candidates per query instead of re-learning its thresholds in every list.
-    constexpr int kMaxPhases = 6;
+    // Launch boundaries (in row tiles).  The first launch covers a small prefix (IVR_MMA_PHASE0_ROWS, 2 k rows), every
+    // further one IVR_MMA_PHASE_RATIO times the rows seen so far, the last one the rest: a launch then admits
+    // ~k * ratio candidates per query instead of re-learning its thresholds in every list.  If the last launch would
+    // still be more than `ratio` times the rows seen before it, one more boundary goes to the geometric mean (1 M rows
+    // at ratio 16: 2 k, 32 k, REST = 30 x was 4.5 ms for 4096 queries against 3.6 ms with an even split).
+    // First launch: 8 k rows until the merges between launches became cheap (topk_merge.cu, flattened select); with
+    // them 2 k rows win on small shards -- 100 k x 1000 queries 0.44 -> 0.32 ms, 1 M x 256 0.49 -> 0.42 ms, 1 M x 1024
+    // 1.16 -> 1.03-1.12 ms -- and are neutral from 10 M rows up (profiles/r2_phase_schedule_after_merge.txt).
+    constexpr int kMaxPhases = 7;
     int64_t bounds[kMaxPhases + 1] = {0};
     int n_phases = 0;
     if (env_int("IVR_MMA_TWO_PHASE", 1)) {
@@ -875,10 +880,14 @@ static int search_mma_batch(ivr_index* idx, const float* q_dev, int64_t nq, int 
         // its thresholds only improve at launch boundaries: it gets more of them (measured, 10 M x 4096 queries:
         // 34.0 ms at ratio 8 vs 35.5 ms at 16; the query-tile-resident kernel prefers 16: 8.4 vs 8.9 ms at 1024 queries)
         const int64_t ratio = std::max(2, env_int("IVR_MMA_PHASE_RATIO", xres ? 8 : 16));
-        int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 8192) / tile_rows);
-        while (n_phases < kMaxPhases - 1 && b * 2 <= nt) {         // a boundary must leave at least as much for later
+        int64_t b = std::max<int64_t>(1, env_int("IVR_MMA_PHASE0_ROWS", 2048) / tile_rows);
+        while (n_phases < kMaxPhases - 2 && b * 2 <= nt) {         // a boundary must leave at least as much for later
             bounds[++n_phases] = b;
             b *= ratio;
+        }
+        if (n_phases > 0 && nt > bounds[n_phases] * ratio) {
+            const int64_t g = static_cast<int64_t>(std::sqrt(static_cast<double>(bounds[n_phases]) * static_cast<double>(nt)));
+            if (g > bounds[n_phases] && g < nt) bounds[++n_phases] = g;
         }
     }
     bounds[++n_phases] = nt;

@@ -369,7 +369,7 @@ def test_topk_merge_kernel_matches_oracle():
     rng = np.random.default_rng(0)
     for n_parts, nq, k in ((8, 33, 100), (2, 5, 7), (130, 3, 20), (3, 4, 1000)):
         D = np.sort(rng.standard_normal((n_parts, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
-        I = np.stack([rng.permutation(10 * k * n_parts)[:nq * k].reshape(nq, k) + p * 10_000_000
+        I = np.stack([np.stack([rng.permutation(10 * k)[:k] for _ in range(nq)]) + p * 10_000_000
                       for p in range(n_parts)]).astype(np.int64)
         I[0, 0, k // 2:] = -1                                   # a short (padded) shard list
         D[0, 0, k // 2:] = flat_ip.NEG_PAD
@@ -415,7 +415,7 @@ def test_packed_key_search_and_key_merge_match_the_unpacked_path():
     rng = np.random.default_rng(3)
     for n_parts, nq, k in ((8, 33, 100), (2, 5, 7), (64, 3, 20), (3, 4, 1000), (64, 2, 300), (40, 2, 100), (8, 1100, 100)):
         D = np.sort(rng.standard_normal((n_parts, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
-        I = np.stack([rng.permutation(10 * k * n_parts)[:nq * k].reshape(nq, k) + p * 10_000_000
+        I = np.stack([np.stack([rng.permutation(10 * k)[:k] for _ in range(nq)]) + p * 10_000_000
                       for p in range(n_parts)]).astype(np.int64)
         I[0, 0, k // 2:] = -1
         D[0, 0, k // 2:] = flat_ip.NEG_PAD
