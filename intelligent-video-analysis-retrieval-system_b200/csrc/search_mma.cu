@@ -991,7 +991,12 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     const int cg = cta_group_mode(nq);
     // measured (10 M rows): 512 dims -- 64 queries 2.0 ms small-batch vs 2.1 ms batched, 80: 2.5 vs 2.2, 128: 3.7 vs 2.3
     // (the resident queries squeeze the row ring); 768 dims -- 64..80 queries 2.4-2.6 ms vs 5.7-6.2 ms
-    const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", idx->dpad <= kMaxKBlocks * kKBlock ? 64 : 128);
+    // Round 2, after the merges between launches became cheap, the batched kernel (single CTAs, M = 128) took over
+    // 17..64 queries on large shards: 10 M rows -- 24 / 32 / 48 / 64 queries 1.72 / 1.73 / 1.76 / 1.76 ms against
+    // 1.80 / 1.78 / 2.12 / 2.19 ms on the small-batch kernel; 30 M x 64: 4.65 vs 5.8-6.4 ms; 3 M rows: equal; below that
+    // the small-batch kernel's one-launch dump mode wins (1 M x 64: 0.32 vs 0.38 ms).
+    const int small_dflt = idx->dpad > kMaxKBlocks * kKBlock ? 128 : (idx->ntotal <= 3500000 ? 64 : 16);
+    const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", small_dflt);
     // beyond 1024 dims only the small-batch kernel exists (its query tile loops over any number of k-blocks)
     if (mode == 3 || ((mode == 0 || !mma_supported(idx, nq, k)) && nq <= small_max && mma_small_supported(idx, nq, k)))
         return search_mma_small(idx, q_dev, nq, k, D_dev, I_dev, id_offset, st);
