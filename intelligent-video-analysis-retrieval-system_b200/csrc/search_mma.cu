@@ -994,8 +994,11 @@ int search_mma(ivr_index* idx, const float* q_dev, int64_t nq, int k, float* D_d
     // Round 2, after the merges between launches became cheap, the batched kernel (single CTAs, M = 128) took over
     // 17..64 queries on large shards: 10 M rows -- 24 / 32 / 48 / 64 queries 1.72 / 1.73 / 1.76 / 1.76 ms against
     // 1.80 / 1.78 / 2.12 / 2.19 ms on the small-batch kernel; 30 M x 64: 4.65 vs 5.8-6.4 ms; 3 M rows: equal; below that
-    // the small-batch kernel's one-launch dump mode wins (1 M x 64: 0.32 vs 0.38 ms).
-    const int small_dflt = idx->dpad > kMaxKBlocks * kKBlock ? 128 : (idx->ntotal <= 3500000 ? 64 : 16);
+    // the small-batch kernel's one-launch dump mode wins (1 M x 64: 0.32 vs 0.38 ms).  At 100 M rows the batched kernel's
+    // HBM rate is erratic (128 queries: 15.1 .. 21.0 ms over four runs; 17 / 32 / 64 queries 16.6 / 17.9 / 18.3 ms against
+    // 15.1-15.8 / ~16 / 17.2-18.1 ms on the small-batch kernel), so the hand-off at 17 queries applies up to 50 M rows.
+    const bool mid_shard = idx->ntotal > 3500000 && idx->ntotal <= 50000000;
+    const int small_dflt = idx->dpad > kMaxKBlocks * kKBlock ? 128 : (mid_shard ? 16 : 64);
     const int small_max = env_int("IVR_MMA_SMALL_MAX_NQ", small_dflt);
     // beyond 1024 dims only the small-batch kernel exists (its query tile loops over any number of k-blocks)
     if (mode == 3 || ((mode == 0 || !mma_supported(idx, nq, k)) && nq <= small_max && mma_small_supported(idx, nq, k)))
