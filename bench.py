@@ -659,7 +659,7 @@ def run_ours(args):
         kall = [torch.empty_like(kt) for _ in range(world)]
         dist.all_gather(kall, kt)
         k_ranks = [float(v.item()) for v in kall]
-    rows_now = [int(v) for v in np.diff(index._bounds)] if margin else None
+    rows_now = index.rows_per_rank if margin else None
     n_local = rows_now[rank] if margin else row1 - row0            # rows this rank scored in the last searches
     path = launches["path"]
     peaks = {}
@@ -752,7 +752,7 @@ def run_ours(args):
                                                 ("status", "max_abs_score_error_vs_exact_fp32", "tie_band_substitutions")}
         log = index.balance_log
         balance = {"elastic_margin_rows": margin, "controller_period_searches": 8, "controller_steps": len(log),
-                   "rows_per_rank_now": [int(v) for v in np.diff(index._bounds)],
+                   "rows_per_rank_now": index.rows_per_rank,
                    "scoring_ms_per_rank_at_last_step": [round(t, 3) for t in log[-1][1]] if log else None,
                    "scoring_ms_per_rank_equal_shards": [round(t, 3) for t in log[0][1]] if log else None}
     if rank == 0:

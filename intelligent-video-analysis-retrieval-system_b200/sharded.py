@@ -357,6 +357,11 @@ class ShardedFlatIP:
     def ntotal(self) -> int:
         return self.ntotal_global
 
+    @property
+    def rows_per_rank(self):
+        """Rows every rank scores in the NEXT search (elastic boundaries), or None for a static partition."""
+        return None if self._bounds is None else [int(v) for v in np.diff(self._bounds)]
+
     def scoring_rate(self, q, k: int, reps: int = 8, warm: int = 3) -> float:
         """Rows per millisecond THIS rank's GPU scores for the batch ``q`` on its current shard (device-timed, local
         search only, no exchange).  All-gather the rates and pass them to ``partition_rows`` / ``add_global`` as

@@ -121,3 +121,29 @@ def test_argument_checks():
     one.wait(0, 1, 0)
     torch.cuda.synchronize()
     one.close()
+
+
+def test_single_rank_sharded_index_front_ends():
+    """Without a process group a ShardedFlatIP is one shard: search / search_async / to_host go straight to the local
+    index (no exchange), with the same hits."""
+    import torch
+    import ivr_b200
+    d, n, k = 128, 9000, 20
+    xb = synth.clip_like(n, d, seed=15, n_centres=32)
+    xq = synth.clip_like(6, d, seed=16, n_centres=32)
+    sh = ivr_b200.ShardedFlatIP(d, device=0)
+    assert sh.world == 1 and sh.rows_per_rank is None
+    sh.add_global(xb)
+    q = torch.from_numpy(xq).cuda()
+    D, I = sh.search(q, k)
+    ref = flat_ip.IndexFlatIP(d)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k)
+    assert not comparator.compare_topk(D.cpu().numpy(), I.cpu().numpy(), Dr, Ir, lambda ids: ref.scores_of(xq, ids), TOL)
+    hD, hI = torch.empty((6, k)).pin_memory(), torch.empty((6, k), dtype=torch.int64).pin_memory()
+    h = sh.search_async(q, k).to_host(hD, hI)
+    h.synchronize()
+    assert torch.equal(hD, D.cpu()) and torch.equal(hI, I.cpu())
+    D2, I2 = sh.search_async(q, k).result(copy=False)
+    torch.cuda.synchronize()
+    assert torch.equal(D2, D) and torch.equal(I2, I)
