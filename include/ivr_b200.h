@@ -100,7 +100,8 @@ IVR_API int ivr_index_search_device(ivr_index* idx, const float* q_dev, int64_t 
  * 12): keys uint64 [nq, k] (device), key = order_preserving(float32 score) << 32 | ~(uint32)(row + id_offset),
  * unsigned descending order = score descending then lower id, key 0 = padding (k > ntotal).  Global row ids
  * must stay below 2^32 (id_offset + ntotal <= 2^32), else IVR_EUNSUPPORTED.  Merged by
- * ivr_topk_merge_keys_device after one all-gather (semantic precedent: system.py:1721-1746). */
+ * ivr_topk_merge_keys_device after the exchange (ivr_exchange_* below, or one all-gather; semantic precedent:
+ * system.py:1721-1746). */
 IVR_API int ivr_index_search_keys_device(ivr_index* idx, const float* q_dev, int64_t nq, int k,
                                  uint64_t* keys_dev, int64_t id_offset, int path, void* stream);
 
