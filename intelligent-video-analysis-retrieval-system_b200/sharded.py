@@ -421,21 +421,29 @@ class ShardedFlatIP:
             dist.barrier(group=self.group)
             self._mail.close()
             self._mail = None
-        mail = _PeerExchange(self.device, self.rank, self.world, n_entries)
-        mine = torch.frombuffer(bytearray(mail.ipc_handle()), dtype=torch.uint8).to(device)
+        # every rank reaches both collectives below whatever happens locally: a rank that cannot create or map a
+        # mailbox reports it through the all-reduce instead of leaving the others waiting
+        mail, err = None, None
+        try:
+            mail = _PeerExchange(self.device, self.rank, self.world, n_entries)
+            handle = mail.ipc_handle()
+        except nat.NativeError as e:
+            err, handle = e, bytes(nat.IVR_IPC_HANDLE_BYTES)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
         allh = torch.empty((self.world, nat.IVR_IPC_HANDLE_BYTES), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        ok = 1
-        try:
-            mail.connect_ipc(allh.cpu().numpy().tobytes())
-        except nat.NativeError:
-            if not self._auto_exchange:
-                raise
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        if err is None:
+            try:
+                mail.connect_ipc(allh.cpu().numpy().tobytes())
+            except nat.NativeError as e:
+                err = e
+        flag = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
-            mail.close()
+            if mail is not None:
+                mail.close()
+            if not self._auto_exchange:
+                raise RuntimeError(f"exchange='peer' is not available on every rank (rank {self.rank}: {err or 'ok'})")
             self.exchange = "nccl"
             return False
         self._mail = mail
