@@ -5,8 +5,12 @@ Metric (BASELINE.json): top-100 queries/sec over N x 512 embeddings at 1/2/4/8 B
 roofline fraction of the dominant kernel.  Workload: BASELINE config D -- 100 M x 512 synthetic
 CLIP-like embeddings (fp16 rows, 102.4 GB: fits ONE B200), a batch of 4096 queries, k = 100.
 Scaling is STRONG: the same 100 M rows are row-sharded over the N ranks (N=8 -> 12.5 M rows per
-GPU, exactly config D), local top-k per GPU, one NCCL all-gather of packed 64-bit keys, on-device
-k-way merge.
+GPU, exactly config D), local top-k per GPU, packed 64-bit keys pushed into every peer's mailbox over NVLink
+(csrc/exchange.cu; one NCCL all-gather where peers cannot be mapped), on-device k-way merge.  At N > 1 two searches
+are in flight -- the exchange and merge of batch i run on a side stream while batch i+1 is being scored -- and the
+shard boundaries follow each GPU's measured scoring speed (elastic boundaries: every rank also stores 4 % of either
+neighbour's rows; `--equal-shards` turns that off).  Every batch is complete, merged and (e2e) back in host memory
+before the closing timestamp.
 
     python bench.py --gpus 1 --steps K --warmup W          # our arm
     python bench.py --impl reference ...                   # the reference's own CPU code path
